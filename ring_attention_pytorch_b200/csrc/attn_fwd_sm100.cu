@@ -1,0 +1,571 @@
+// Fused ring flash-attention forward for sm_100a.
+//
+// One persistent, warp-specialised CTA per SM (384 threads):
+//   warp 0      TMA producer   : Q tiles and K/V tiles (128B-swizzled tensor-map boxes) -> shared memory
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma  S = Q K^T (SS)  and  O += P V (TS, P in TMEM)
+//   warp 2      ring fetcher   : pulls the other ring ranks' K/V slots over NVLink with bulk-TMA copies
+//                                (peer global -> smem -> local global) and publishes per-owner ready counters
+//   warps 4-7   softmax WG 0   : one thread per query row of Q tile 0 (TMEM lane == row)
+//   warps 8-11  softmax WG 1   : same for Q tile 1; the two tiles ping-pong on the tensor core
+//
+// TMEM (512 columns): S0 | S1 (128 fp32 columns each, P aliases the first 64 columns as packed 16-bit)
+//                     O0 | O1 (D fp32 columns each).  O, the running max and the running sum stay in
+// TMEM / registers across every hop of the ring, so nothing is re-normalised or round-tripped through
+// HBM between hops (reference: ring_flash_attention_cuda.py:136-186 carries o/m/lse through global
+// memory in 16 bit and launches one Triton kernel + one NCCL exchange + barrier per hop).
+//
+// The ring itself is only a schedule: ring rank r visits owners hop_owner[0..hop_count) (itself first).
+// K/V of owner o live in slot o of a symmetric [world][2][b*hk][n][d] buffer.  Slot r is written locally
+// by pack_kv; the other slots are filled inside this kernel by the fetcher warps of all CTAs (each moves
+// 1/gridDim of every slot), overlapping the NVLink transfer with the MMAs of earlier hops.  Layout
+// (plain / striped / zig-zag), causal + sliding-window masking and key padding are position functions
+// evaluated in-kernel; fully masked tiles are never loaded.
+#include "attn_common.cuh"
+
+namespace rab {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int NSLOT = 4;
+constexpr int FETCH_PIECE = 16384;
+constexpr int NTHREADS = 384;
+constexpr int SUB_BYTES = 128 * 128;  // one 64-element-wide, 128-row swizzled sub-tile
+
+template <int D>
+struct FwdSmem {
+  static constexpr int NSUB = D / 64;
+  static constexpr int TILE_BYTES = NSUB * SUB_BYTES;
+  alignas(1024) uint8_t q[2][TILE_BYTES];
+  alignas(1024) uint8_t kv[NSLOT][TILE_BYTES];
+  alignas(1024) uint8_t fetch[2][FETCH_PIECE];
+  uint64_t q_full[2], q_empty[2];
+  uint64_t kv_full[NSLOT], kv_empty[NSLOT];
+  uint64_t s_full[2], p_ready[2], o_done[2], epi_done[2];
+  uint64_t fetch_full[2];
+  uint32_t tmem_base;
+};
+
+struct Item {
+  int b, h, kvh, qp;
+  int row0[2];
+  bool tvalid[2];
+  int qlo[2], qhi[2];
+};
+
+struct TileInfo {
+  int owner, kt;
+  bool need[2], part[2];
+};
+
+__device__ __forceinline__ int num_items(const AttnFwdParams& p) {
+  const int nqp = (p.n_q + 2 * BM - 1) / (2 * BM);
+  return p.batch * p.heads * nqp;
+}
+
+// Work items are ordered heaviest-first (largest q index first under causal masking) and, inside one
+// q-pair, so that query heads sharing a KV head are adjacent (L2 reuse of the K/V tiles).
+__device__ __forceinline__ void decode_item(const AttnFwdParams& p, int idx, Item& it) {
+  const int bh = p.batch * p.heads;
+  const int nqp = (p.n_q + 2 * BM - 1) / (2 * BM);
+  it.qp = nqp - 1 - idx / bh;
+  const int r = idx % bh;
+  it.b = r / p.heads;
+  const int hh = r % p.heads;
+  const int groups = p.heads / p.kv_heads;
+  it.kvh = hh / groups;
+  it.h = (hh % groups) * p.kv_heads + it.kvh;  // reference mapping: query head j uses kv head j % kv_heads
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    it.row0[t] = it.qp * 2 * BM + t * BM;
+    it.tvalid[t] = it.row0[t] < p.n_q;
+    if (it.tvalid[t]) {
+      pos_range(p.pos, p.rank, it.row0[t], min(it.row0[t] + BM, p.n_q) - 1, it.qlo[t], it.qhi[t]);
+      it.qlo[t] += p.q_pos_offset;
+      it.qhi[t] += p.q_pos_offset;
+    } else {
+      it.qlo[t] = it.qhi[t] = 0;
+    }
+  }
+}
+
+struct KvIter {
+  int s = 0, kt = 0;
+  __device__ __forceinline__ bool next(const AttnFwdParams& p, const Item& it, TileInfo& ti) {
+    const int nkt = (p.n_k + BN - 1) / BN;
+    const MaskCfg mc{p.causal, p.window, p.kmask_bits != nullptr};
+    while (s < p.hop_count) {
+      const int o = p.hop_owner[s];
+      while (kt < nkt) {
+        const int k = kt++;
+        const int a = k * BN, bb = min(a + BN, p.n_k) - 1;
+        int klo, khi;
+        pos_range(p.pos, o, a, bb, klo, khi);
+        const bool tail = (a + BN) > p.n_k;
+        bool any = false;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          bool need = false, part = false;
+          if (it.tvalid[t]) classify_tile(mc, it.qlo[t], it.qhi[t], klo, khi, tail, need, part);
+          ti.need[t] = need;
+          ti.part[t] = part;
+          any |= need;
+        }
+        if (any) {
+          ti.owner = o;
+          ti.kt = k;
+          return true;
+        }
+      }
+      kt = 0;
+      ++s;
+    }
+    return false;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// warp 0: TMA producer
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void producer_role(FwdSmem<D>& sm, const AttnFwdParams& p, const CUtensorMap* map_q,
+                              const CUtensorMap* map_kv) {
+  constexpr int NSUB = FwdSmem<D>::NSUB;
+  constexpr uint32_t TILE_BYTES = FwdSmem<D>::TILE_BYTES;
+  uint32_t n_slot = 0;
+  uint32_t items_t[2] = {0, 0};
+  uint32_t ready_mask = 1u << p.rank;
+  const int total = num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+    Item it;
+    decode_item(p, idx, it);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (!it.tvalid[t]) continue;
+      mbar_wait(&sm.q_empty[t], (items_t[t] & 1) ^ 1, 100 + t);
+      mbar_expect_tx(&sm.q_full[t], TILE_BYTES);
+#pragma unroll
+      for (int s = 0; s < NSUB; ++s)
+        tma_load_4d(sm.q[t] + s * SUB_BYTES, map_q, &sm.q_full[t], s * 64, it.h, it.row0[t], it.b);
+      items_t[t]++;
+    }
+    KvIter iter;
+    TileInfo ti;
+    while (iter.next(p, it, ti)) {
+      if (!((ready_mask >> ti.owner) & 1u)) {
+        spin_until_ge_gpu(&p.ready[ti.owner], gridDim.x, 110);
+        fence_proxy_async_global();
+        ready_mask |= 1u << ti.owner;
+      }
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t slot = n_slot % NSLOT, ph = (n_slot / NSLOT) & 1;
+        mbar_wait(&sm.kv_empty[slot], ph ^ 1, 120 + slot);
+        mbar_expect_tx(&sm.kv_full[slot], TILE_BYTES);
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s)
+          tma_load_4d(sm.kv[slot] + s * SUB_BYTES, map_kv, &sm.kv_full[slot], s * 64, ti.kt * BN,
+                      it.b * p.kv_heads + it.kvh, ti.owner * 2 + which);
+        n_slot++;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp 1: MMA issuer
+// ------------------------------------------------------------------------------------------------
+template <int D, bool BF16>
+__device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p, uint32_t tmem) {
+  constexpr uint32_t idesc_qk = umma_idesc_bf16(BM, BN, 0, 0, BF16 ? 1 : 0);
+  constexpr uint32_t idesc_pv = umma_idesc_bf16(BM, D, 0, 1, BF16 ? 1 : 0);
+  // K-major operands (Q, K): 8-row groups 1024 B apart; the leading offset is unused with 128B swizzle.
+  constexpr uint64_t kmaj_static = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
+  // MN-major operand (V as B of P V): 64-wide d sub-tiles SUB_BYTES apart, 8-row kv groups 1024 B apart.
+  constexpr uint64_t vmaj_static = umma_smem_desc_hi_lo(SUB_BYTES, 1024, UMMA_LAYOUT_SW128);
+
+  uint32_t n_kv = 0;
+  uint32_t cnt_p[2] = {0, 0};
+  uint32_t items_t[2] = {0, 0};
+  const uint32_t s_tm[2] = {tmem + 0, tmem + 128};
+  const uint32_t o_tm[2] = {tmem + 256, tmem + 256 + D};
+
+  auto issue_qk = [&](int t, uint32_t kslot) {
+    const uint32_t qa = smem_u32(sm.q[t]);
+    const uint32_t ka = smem_u32(sm.kv[kslot]);
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      const uint32_t off = (kk / 4) * SUB_BYTES + (kk % 4) * 32;
+      umma_ss(s_tm[t], umma_desc(kmaj_static, qa + off), umma_desc(kmaj_static, ka + off), idesc_qk, kk > 0);
+    }
+    umma_commit(&sm.s_full[t]);
+  };
+
+  const int total = num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+    Item it;
+    decode_item(p, idx, it);
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (it.tvalid[t]) mbar_wait(&sm.q_full[t], items_t[t] & 1, 200 + t);
+    tc_fence_after();
+
+    KvIter iter;
+    TileInfo cur, nxt;
+    bool has = iter.next(p, it, cur);
+    bool pv_started[2] = {false, false};
+    if (has) {
+      const uint32_t ks = (2 * n_kv) % NSLOT, kph = ((2 * n_kv) / NSLOT) & 1;
+      mbar_wait(&sm.kv_full[ks], kph, 210);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (cur.need[t]) issue_qk(t, ks);
+      umma_commit(&sm.kv_empty[ks]);
+    }
+    while (has) {
+      const bool hasn = iter.next(p, it, nxt);
+      const uint32_t vs = (2 * n_kv + 1) % NSLOT, vph = ((2 * n_kv + 1) / NSLOT) & 1;
+      const uint32_t ksn = (2 * n_kv + 2) % NSLOT, kphn = ((2 * n_kv + 2) / NSLOT) & 1;
+      mbar_wait(&sm.kv_full[vs], vph, 220);
+      tc_fence_after();
+      bool kwaited = false;
+      const uint32_t va = smem_u32(sm.kv[vs]);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (cur.need[t]) {
+          if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 230 + t);
+          mbar_wait(&sm.p_ready[t], cnt_p[t] & 1, 240 + t);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            umma_ts(o_tm[t], s_tm[t] + kk * 8, umma_desc(vmaj_static, va + kk * 2048), idesc_pv,
+                    (pv_started[t] || kk > 0) ? 1u : 0u);
+          }
+          pv_started[t] = true;
+          umma_commit(&sm.o_done[t]);
+          cnt_p[t]++;
+        }
+        if (hasn && nxt.need[t]) {
+          if (!kwaited) {
+            mbar_wait(&sm.kv_full[ksn], kphn, 250);
+            tc_fence_after();
+            kwaited = true;
+          }
+          issue_qk(t, ksn);
+        }
+      }
+      umma_commit(&sm.kv_empty[vs]);
+      if (hasn) umma_commit(&sm.kv_empty[ksn]);
+      n_kv++;
+      cur = nxt;
+      has = hasn;
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (!it.tvalid[t]) continue;
+      if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 260 + t);
+      umma_commit(&sm.q_empty[t]);
+      items_t[t]++;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp 2: ring fetcher (peer K/V slot -> local slot, 1/gridDim of every slot per CTA)
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void fetch_role(FwdSmem<D>& sm, const AttnFwdParams& p) {
+  uint32_t fcount = 0;
+  const unsigned long long npieces = (p.slot_bytes + FETCH_PIECE - 1) / FETCH_PIECE;
+  for (int s = 1; s < p.hop_count; ++s) {
+    const int o = p.hop_owner[s];
+    const uint8_t* src = p.kv_peer[o] + (unsigned long long)o * p.slot_bytes;
+    uint8_t* dst = p.kv_local + (unsigned long long)o * p.slot_bytes;
+    auto piece_bytes = [&](unsigned long long pc) -> uint32_t {
+      const unsigned long long rem = p.slot_bytes - pc * FETCH_PIECE;
+      return rem < (unsigned long long)FETCH_PIECE ? (uint32_t)rem : (uint32_t)FETCH_PIECE;
+    };
+    unsigned long long pc = blockIdx.x;
+    if (pc < npieces) {
+      // software pipeline: load(i+1) is in flight while load(i) is drained to local memory
+      bulk_wait_read<0>();
+      {
+        const uint32_t buf = fcount & 1;
+        const uint32_t bytes = piece_bytes(pc);
+        mbar_expect_tx(&sm.fetch_full[buf], bytes);
+        bulk_load_1d(sm.fetch[buf], src + pc * FETCH_PIECE, bytes, &sm.fetch_full[buf]);
+      }
+      while (pc < npieces) {
+        const unsigned long long pn = pc + gridDim.x;
+        if (pn < npieces) {
+          bulk_wait_read<0>();  // the store that last read the other buffer has drained it
+          const uint32_t buf = (fcount + 1) & 1;
+          const uint32_t bytes = piece_bytes(pn);
+          mbar_expect_tx(&sm.fetch_full[buf], bytes);
+          bulk_load_1d(sm.fetch[buf], src + pn * FETCH_PIECE, bytes, &sm.fetch_full[buf]);
+        }
+        const uint32_t buf = fcount & 1;
+        mbar_wait(&sm.fetch_full[buf], (fcount >> 1) & 1, 300 + buf);
+        bulk_store_1d(dst + pc * FETCH_PIECE, sm.fetch[buf], piece_bytes(pc));
+        bulk_commit();
+        fcount++;
+        pc = pn;
+      }
+      bulk_wait<0>();  // all stores of this owner's slot are complete
+    }
+    fence_proxy_async_global();
+    __threadfence();
+    red_release_gpu_add(&p.ready[o], 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warps 4-11: softmax / correction / epilogue, one thread per query row
+// ------------------------------------------------------------------------------------------------
+template <int D, bool BF16, int t>
+__device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams& p, uint32_t tmem) {
+  const int wg_tid = threadIdx.x - (128 + 128 * t);
+  const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
+  const uint32_t s_tm = tmem + t * 128 + lane_off;
+  const uint32_t o_tm = tmem + 256 + t * D + lane_off;
+  uint32_t cnt = 0;
+
+  const bool clamp = p.softclamp > 0.f;
+  const float mul = clamp ? 1.f : p.scale * kLog2e;
+  const float pre = clamp ? p.scale / p.softclamp : 0.f;
+  const float post = clamp ? p.softclamp * kLog2e : 0.f;
+
+  const int total = num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+    Item it;
+    decode_item(p, idx, it);
+    if (!it.tvalid[t]) continue;
+    const int grow = it.row0[t] + wg_tid;
+    const bool row_ok = grow < p.n_q;
+    const int pos_q = pos_of(p.pos, p.rank, min(grow, p.n_q - 1)) + p.q_pos_offset;
+
+    float m_used = -INFINITY;
+    float l = 0.f;
+    bool have_o = false;
+    uint32_t cnt_item = 0;
+
+    KvIter iter;
+    TileInfo ti;
+    while (iter.next(p, it, ti)) {
+      if (!ti.need[t]) continue;
+      mbar_wait(&sm.s_full[t], cnt & 1, 400 + t);
+      tc_fence_after();
+      uint32_t sr[128];
+      tmem_ld32(s_tm + 0, sr + 0);
+      tmem_ld32(s_tm + 32, sr + 32);
+      tmem_ld32(s_tm + 64, sr + 64);
+      tmem_ld32(s_tm + 96, sr + 96);
+      tc_wait_ld();
+
+      if (clamp) {
+#pragma unroll
+        for (int j = 0; j < 128; ++j) sr[j] = __float_as_uint(fast_tanh(__uint_as_float(sr[j]) * pre) * post);
+      }
+      if (ti.part[t]) {
+        const int c0 = ti.kt * BN;
+        const int split = p.pos.seg_len - c0;
+        const int a0 = p.pos.base0[ti.owner] + p.pos.stride * c0;
+        const int a1 = p.pos.base1[ti.owner] + p.pos.stride * (c0 - p.pos.seg_len);
+        uint32_t mb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (p.kmask_bits != nullptr) {
+          const uint32_t* w =
+              p.kmask_bits + ((size_t)ti.owner * p.batch + it.b) * p.kmask_words + (size_t)ti.kt * 4;
+          mb[0] = w[0]; mb[1] = w[1]; mb[2] = w[2]; mb[3] = w[3];
+        }
+        const int ncols = p.n_k - c0;  // columns >= ncols are beyond the end of the slot
+#pragma unroll
+        for (int j = 0; j < 128; ++j) {
+          const int pk = (j < split ? a0 : a1) + p.pos.stride * j;
+          bool keep = (j < ncols) && ((mb[j >> 5] >> (j & 31)) & 1u);
+          if (p.causal) {
+            keep = keep && (pk <= pos_q);
+            if (p.window > 0) keep = keep && (pos_q - pk <= p.window);
+          }
+          if (!keep) sr[j] = 0xff800000u;  // -inf
+        }
+      }
+
+      float mx = __uint_as_float(sr[0]);
+#pragma unroll
+      for (int j = 1; j < 128; ++j) mx = fmaxf(mx, __uint_as_float(sr[j]));
+      mx *= mul;
+
+      // lazy rescale: only when the running max moved by more than 2^8 (warp-uniform decision)
+      const bool need_rs = mx > m_used + 8.f;
+      if (__any_sync(0xffffffffu, need_rs)) {
+        const float m_new = fmaxf(m_used, mx);
+        const float factor = (m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_new);
+        l *= factor;
+        if (have_o) {
+          // the previous P V of this tile completed before S became visible (commit ordering)
+#pragma unroll
+          for (int c = 0; c < D; c += 32) {
+            uint32_t orr[32];
+            tmem_ld32(o_tm + c, orr);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * factor);
+            tmem_st32(o_tm + c, orr);
+          }
+        }
+        m_used = m_new;
+      }
+      const float m_eff = (m_used == -INFINITY) ? 0.f : m_used;
+      float lsum0 = 0.f, lsum1 = 0.f;
+      uint32_t pk2[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[2 * j]), mul, -m_eff));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[2 * j + 1]), mul, -m_eff));
+        lsum0 += p0;
+        lsum1 += p1;
+        pk2[j] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+      }
+      l += lsum0 + lsum1;
+      tmem_st32(s_tm + 0, pk2);
+      tmem_st32(s_tm + 32, pk2 + 32);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&sm.p_ready[t]);
+      cnt++;
+      cnt_item++;
+      have_o = true;
+    }
+
+    // epilogue: O / l -> 16 bit, lse
+    if (cnt_item > 0) {
+      mbar_wait(&sm.o_done[t], (cnt - 1) & 1, 410 + t);
+      tc_fence_after();
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
+                                           (((size_t)it.b * p.n_q + (row_ok ? grow : 0)) * p.heads + it.h) * D);
+#pragma unroll
+    for (int c = 0; c < D; c += 32) {
+      uint32_t orr[32];
+      if (cnt_item > 0) {
+        tmem_ld32(o_tm + c, orr);
+        tc_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) orr[i] = 0u;
+      }
+      uint32_t w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = __uint_as_float(orr[2 * i]) * inv, bq = __uint_as_float(orr[2 * i + 1]) * inv;
+        w[i] = BF16 ? pack_bf16x2(a, bq) : pack_f16x2(a, bq);
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) orow[c / 8 + i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      }
+    }
+    if (row_ok) {
+      const float m_eff = (m_used == -INFINITY) ? 0.f : m_used;
+      p.lse[((size_t)it.b * p.heads + it.h) * p.n_q + grow] = l > 0.f ? (m_eff + log2f(l)) * kLn2 : INFINITY;
+    }
+    tc_fence_before();
+    mbar_arrive(&sm.epi_done[t]);
+  }
+}
+
+template <int D, bool BF16>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                const __grid_constant__ AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  FwdSmem<D>& sm =
+      *reinterpret_cast<FwdSmem<D>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x / 32;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.q_full[i], 1);
+      mbar_init(&sm.q_empty[i], 1);
+      mbar_init(&sm.s_full[i], 1);
+      mbar_init(&sm.p_ready[i], 128);
+      mbar_init(&sm.o_done[i], 1);
+      mbar_init(&sm.epi_done[i], 128);
+      mbar_init(&sm.fetch_full[i], 1);
+    }
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(&sm.kv_full[i], 1);
+      mbar_init(&sm.kv_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane_id() == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_kv);
+  }
+  if (warp == 2) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < 4) {
+    setmaxnreg_dec<72>();
+    if (lane_id() == 0) {
+      if (warp == 0) {
+        producer_role<D>(sm, p, &map_q, &map_kv);
+      } else if (warp == 1) {
+        mma_role<D, BF16>(sm, p, tmem);
+      } else if (warp == 2) {
+        fetch_role<D>(sm, p);
+      }
+    }
+  } else {
+    setmaxnreg_inc<216>();
+    if (warp < 8) {
+      softmax_role<D, BF16, 0>(sm, p, tmem);
+    } else {
+      softmax_role<D, BF16, 1>(sm, p, tmem);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+size_t attn_fwd_smem_bytes(int head_dim) {
+  return (head_dim == 128 ? sizeof(FwdSmem<128>) : sizeof(FwdSmem<64>)) + 1024;
+}
+
+template <int D>
+void launch_attn_fwd(const CUtensorMap& map_q, const CUtensorMap& map_kv, const AttnFwdParams& p, int num_sms,
+                     cudaStream_t stream) {
+  auto kern = p.is_bf16 ? attn_fwd_kernel<D, true> : attn_fwd_kernel<D, false>;
+  const size_t smem = sizeof(FwdSmem<D>) + 1024;
+  cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+             "attn_fwd smem attribute");
+  const int nqp = (p.n_q + 2 * BM - 1) / (2 * BM);
+  const int items = p.batch * p.heads * nqp;
+  void* args[] = {(void*)&map_q, (void*)&map_kv, (void*)&p};
+  if (p.hop_count > 1) {
+    // every CTA owns a share of the NVLink fetch and other CTAs spin on it: all CTAs must be co-resident
+    cuda_check(cudaLaunchCooperativeKernel((void*)kern, dim3(num_sms), dim3(NTHREADS), args, smem, stream),
+               "attn_fwd cooperative launch");
+  } else {
+    const int grid = items < num_sms ? items : num_sms;
+    cuda_check(cudaLaunchKernel((void*)kern, dim3(grid), dim3(NTHREADS), args, smem, stream), "attn_fwd launch");
+  }
+}
+
+template void launch_attn_fwd<64>(const CUtensorMap&, const CUtensorMap&, const AttnFwdParams&, int, cudaStream_t);
+template void launch_attn_fwd<128>(const CUtensorMap&, const CUtensorMap&, const AttnFwdParams&, int, cudaStream_t);
+
+}  // namespace rab

@@ -1,0 +1,231 @@
+// torch.ops.rab.* bindings.  Only this file sees torch headers.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+#include <torch/torch.h>
+
+#include <vector>
+
+#include "kernels.h"
+#include "symm.h"
+
+namespace {
+
+using torch::Tensor;
+
+int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+void check_16bit(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kBFloat16 || t.scalar_type() == at::kHalf, name, " must be bf16 or fp16");
+}
+
+// ---------------------------------------------------------------------------------------------
+// descriptor probe
+// ---------------------------------------------------------------------------------------------
+Tensor umma_probe(const Tensor& a, const Tensor& b, int64_t mode, int64_t n, int64_t k, int64_t idesc,
+                  int64_t a_lbo, int64_t a_sbo, int64_t b_lbo, int64_t b_sbo, int64_t b_kstep) {
+  check_16bit(a, "a");
+  check_16bit(b, "b");
+  TORCH_CHECK(a.is_contiguous() && b.is_contiguous());
+  TORCH_CHECK(a.size(0) == 128 && a.size(1) == k);
+  c10::cuda::CUDAGuard guard(a.device());
+  uint64_t adims[2] = {(uint64_t)k, 128};
+  uint64_t astr[1] = {(uint64_t)k * 2};
+  uint32_t abox[2] = {64, 128};
+  CUtensorMap map_a = rab::make_tmap_bf16(a.data_ptr(), 2, adims, astr, abox, rab::TmapSwizzle::B128);
+  CUtensorMap map_b;
+  if (mode == 0) {
+    TORCH_CHECK(b.size(0) == n && b.size(1) == k);
+    uint64_t bdims[2] = {(uint64_t)k, (uint64_t)n};
+    uint64_t bstr[1] = {(uint64_t)k * 2};
+    uint32_t bbox[2] = {64, (uint32_t)n};
+    map_b = rab::make_tmap_bf16(b.data_ptr(), 2, bdims, bstr, bbox, rab::TmapSwizzle::B128);
+  } else {
+    TORCH_CHECK(b.size(0) == k && b.size(1) == n);
+    uint64_t bdims[2] = {(uint64_t)n, (uint64_t)k};
+    uint64_t bstr[1] = {(uint64_t)n * 2};
+    uint32_t bbox[2] = {64, (uint32_t)k};
+    map_b = rab::make_tmap_bf16(b.data_ptr(), 2, bdims, bstr, bbox, rab::TmapSwizzle::B128);
+  }
+  rab::ProbeParams p;
+  p.mode = (int)mode;
+  p.n = (int)n;
+  p.k = (int)k;
+  p.idesc = (uint32_t)idesc;
+  p.a_lbo = (uint32_t)a_lbo;
+  p.a_sbo = (uint32_t)a_sbo;
+  p.b_lbo = (uint32_t)b_lbo;
+  p.b_sbo = (uint32_t)b_sbo;
+  p.b_kstep_bytes = (uint32_t)b_kstep;
+  Tensor out = torch::empty({128, n}, a.options().dtype(at::kFloat));
+  rab::launch_umma_probe(map_a, map_b, p, a.data_ptr(), out.data_ptr<float>(), at::cuda::getCurrentCUDAStream());
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused ring attention forward
+// ---------------------------------------------------------------------------------------------
+void fill_posmap(rab::PosMap& pm, int64_t stride, int64_t seg_len, at::IntArrayRef base0, at::IntArrayRef base1,
+                 int world) {
+  pm.stride = (int)stride;
+  pm.seg_len = (int)seg_len;
+  TORCH_CHECK((int)base0.size() == world && (int)base1.size() == world, "position map needs one base per rank");
+  for (int i = 0; i < rab::kMaxWorld; ++i) {
+    pm.base0[i] = i < world ? (int)base0[i] : 0;
+    pm.base1[i] = i < world ? (int)base1[i] : 0;
+  }
+}
+
+std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& kv_buf, at::IntArrayRef peer_ptrs,
+                                    const Tensor& ready, const c10::optional<Tensor>& kmask_bits,
+                                    int64_t kv_heads, int64_t rank, bool causal, int64_t window, double scale,
+                                    double softclamp, int64_t pos_stride, int64_t seg_len, at::IntArrayRef base0,
+                                    at::IntArrayRef base1, int64_t q_pos_offset, at::IntArrayRef hop_owner) {
+  check_16bit(q, "q");
+  check_16bit(kv_buf, "kv_buf");
+  TORCH_CHECK(q.dim() == 4 && q.is_contiguous(), "q must be contiguous [b, n, h, d]");
+  TORCH_CHECK(kv_buf.dim() == 5 && kv_buf.is_contiguous(), "kv_buf must be contiguous [world, 2, b*hk, n_k, d]");
+  TORCH_CHECK(kv_buf.scalar_type() == q.scalar_type());
+  const int b = q.size(0), n_q = q.size(1), h = q.size(2), d = q.size(3);
+  const int world = kv_buf.size(0), n_k = kv_buf.size(3);
+  TORCH_CHECK(kv_buf.size(1) == 2 && kv_buf.size(2) == b * kv_heads && kv_buf.size(4) == d);
+  TORCH_CHECK(d == 64 || d == 128, "head dim must be 64 or 128");
+  TORCH_CHECK(h % kv_heads == 0);
+  TORCH_CHECK(world <= rab::kMaxWorld && (int)peer_ptrs.size() == world);
+  TORCH_CHECK(ready.is_cuda() && ready.scalar_type() == at::kInt && ready.numel() >= world);
+  TORCH_CHECK(hop_owner.size() >= 1 && (int)hop_owner.size() <= world && hop_owner[0] == rank);
+  c10::cuda::CUDAGuard guard(q.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+
+  Tensor o = torch::empty_like(q);
+  Tensor lse = torch::empty({b, h, n_q}, q.options().dtype(at::kFloat));
+
+  rab::AttnFwdParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.batch = b; p.heads = h; p.kv_heads = (int)kv_heads;
+  p.n_q = n_q; p.n_k = n_k; p.world = world; p.rank = (int)rank;
+  p.causal = causal; p.window = (int)window;
+  p.is_bf16 = q.scalar_type() == at::kBFloat16;
+  p.scale = (float)scale; p.softclamp = (float)softclamp;
+  fill_posmap(p.pos, pos_stride, seg_len, base0, base1, world);
+  p.q_pos_offset = (int)q_pos_offset;
+  p.hop_count = (int)hop_owner.size();
+  for (int i = 0; i < p.hop_count; ++i) p.hop_owner[i] = (int)hop_owner[i];
+  p.o = o.data_ptr();
+  p.lse = lse.data_ptr<float>();
+  if (kmask_bits.has_value()) {
+    const Tensor& km = *kmask_bits;
+    TORCH_CHECK(km.is_cuda() && km.scalar_type() == at::kInt && km.is_contiguous() && km.dim() == 3);
+    TORCH_CHECK(km.size(0) == world && km.size(1) == b && km.size(2) % 4 == 0 && km.size(2) * 32 >= n_k);
+    p.kmask_bits = reinterpret_cast<const uint32_t*>(km.data_ptr<int>());
+    p.kmask_words = km.size(2);
+  }
+  p.kv_local = reinterpret_cast<uint8_t*>(kv_buf.data_ptr());
+  for (int i = 0; i < world; ++i)
+    p.kv_peer[i] = peer_ptrs[i] ? reinterpret_cast<const uint8_t*>(peer_ptrs[i]) : p.kv_local;
+  p.slot_bytes = 2ull * b * kv_heads * n_k * d * 2;
+  p.ready = reinterpret_cast<uint32_t*>(ready.data_ptr<int>());
+  rab::cuda_check(cudaMemsetAsync(p.ready, 0, sizeof(uint32_t) * world, stream), "ready memset");
+
+  // Q: [b, n, h, d] -> dims (d, h, n, b), box (64, 1, 128, 1)
+  uint64_t qdims[4] = {(uint64_t)d, (uint64_t)h, (uint64_t)n_q, (uint64_t)b};
+  uint64_t qstr[3] = {(uint64_t)d * 2, (uint64_t)h * d * 2, (uint64_t)n_q * h * d * 2};
+  uint32_t qbox[4] = {64, 1, 128, 1};
+  CUtensorMap map_q = rab::make_tmap_bf16(q.data_ptr(), 4, qdims, qstr, qbox, rab::TmapSwizzle::B128);
+  // KV: [world, 2, b*hk, n_k, d] -> dims (d, n_k, b*hk, 2*world), box (64, 128, 1, 1)
+  uint64_t kdims[4] = {(uint64_t)d, (uint64_t)n_k, (uint64_t)b * kv_heads, (uint64_t)2 * world};
+  uint64_t kstr[3] = {(uint64_t)d * 2, (uint64_t)n_k * d * 2, (uint64_t)b * kv_heads * n_k * d * 2};
+  uint32_t kbox[4] = {64, 128, 1, 1};
+  CUtensorMap map_kv = rab::make_tmap_bf16(kv_buf.data_ptr(), 4, kdims, kstr, kbox, rab::TmapSwizzle::B128);
+
+  if (d == 128) {
+    rab::launch_attn_fwd<128>(map_q, map_kv, p, sm_count(), stream);
+  } else {
+    rab::launch_attn_fwd<64>(map_q, map_kv, p, sm_count(), stream);
+  }
+  return {o, lse};
+}
+
+void pack_kv(const Tensor& k, const Tensor& v, Tensor slot) {
+  check_16bit(k, "k");
+  check_16bit(v, "v");
+  TORCH_CHECK(k.dim() == 4 && v.dim() == 4 && k.sizes() == v.sizes());
+  TORCH_CHECK(k.stride(3) == 1 && v.stride(3) == 1, "k/v need unit stride on the head dim");
+  const int b = k.size(0), n = k.size(1), hk = k.size(2), d = k.size(3);
+  TORCH_CHECK(d % 8 == 0);
+  for (int i = 0; i < 3; ++i)
+    TORCH_CHECK(k.stride(i) % 8 == 0 && v.stride(i) % 8 == 0, "k/v strides must be multiples of 8 elements");
+  TORCH_CHECK(slot.is_contiguous() && slot.numel() == 2ll * b * n * hk * d && slot.scalar_type() == k.scalar_type());
+  c10::cuda::CUDAGuard guard(k.device());
+  rab::launch_pack_kv(k.data_ptr(), v.data_ptr(), slot.data_ptr(), b, n, hk, d, k.stride(0), k.stride(1), k.stride(2),
+                      v.stride(0), v.stride(1), v.stride(2), at::cuda::getCurrentCUDAStream());
+}
+
+void device_barrier(at::IntArrayRef pad_ptrs, int64_t rank, int64_t epoch) {
+  rab::BarrierParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.world = (int)pad_ptrs.size();
+  TORCH_CHECK(p.world <= rab::kMaxWorld);
+  p.rank = (int)rank;
+  p.epoch = (uint32_t)epoch;
+  for (int i = 0; i < p.world; ++i) p.pads[i] = reinterpret_cast<uint32_t*>(pad_ptrs[i]);
+  rab::launch_device_barrier(p, at::cuda::getCurrentCUDAStream());
+}
+
+// ---------------------------------------------------------------------------------------------
+// symmetric memory
+// ---------------------------------------------------------------------------------------------
+std::tuple<Tensor, Tensor> symm_alloc(int64_t bytes) {
+  Tensor handle = torch::empty({rab::kIpcHandleBytes}, torch::dtype(torch::kUInt8));
+  void* base = rab::symm_alloc((size_t)bytes, handle.data_ptr<uint8_t>());
+  int dev = 0;
+  cudaGetDevice(&dev);
+  Tensor t = torch::from_blob(
+      base, {bytes}, [base](void*) { rab::symm_free(base); },
+      torch::TensorOptions().dtype(torch::kUInt8).device(torch::kCUDA, dev));
+  return {t, handle};
+}
+
+int64_t symm_open(const Tensor& handle) {
+  TORCH_CHECK(!handle.is_cuda() && handle.scalar_type() == torch::kUInt8 && handle.numel() == rab::kIpcHandleBytes);
+  return reinterpret_cast<int64_t>(rab::symm_open(handle.contiguous().data_ptr<uint8_t>()));
+}
+
+void symm_close(int64_t ptr) { rab::symm_close(reinterpret_cast<void*>(ptr)); }
+
+}  // namespace
+
+TORCH_LIBRARY(rab, m) {
+  m.def("umma_probe(Tensor a, Tensor b, int mode, int n, int k, int idesc, int a_lbo, int a_sbo, int b_lbo, int "
+        "b_sbo, int b_kstep) -> Tensor");
+  m.def("attn_fwd(Tensor q, Tensor kv_buf, int[] peer_ptrs, Tensor ready, Tensor? kmask_bits, int kv_heads, int rank, "
+        "bool causal, int window, float scale, float softclamp, int pos_stride, int seg_len, int[] base0, int[] "
+        "base1, int q_pos_offset, int[] hop_owner) -> (Tensor, Tensor)");
+  m.def("pack_kv(Tensor k, Tensor v, Tensor(a!) slot) -> ()");
+  m.def("device_barrier(int[] pad_ptrs, int rank, int epoch) -> ()");
+  m.def("symm_alloc(int bytes) -> (Tensor, Tensor)");
+  m.def("symm_open(Tensor handle) -> int");
+  m.def("symm_close(int ptr) -> ()");
+}
+
+TORCH_LIBRARY_IMPL(rab, CUDA, m) {
+  m.impl("umma_probe", &umma_probe);
+  m.impl("attn_fwd", &attn_fwd);
+  m.impl("pack_kv", &pack_kv);
+}
+
+TORCH_LIBRARY_IMPL(rab, CompositeExplicitAutograd, m) {
+  m.impl("device_barrier", &device_barrier);
+  m.impl("symm_alloc", &symm_alloc);
+  m.impl("symm_open", &symm_open);
+  m.impl("symm_close", &symm_close);
+}

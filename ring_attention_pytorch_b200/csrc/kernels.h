@@ -1,0 +1,98 @@
+// Plain C++/CUDA launch API shared between the .cu kernels and the torch bindings.
+// Nothing in here depends on torch headers, so kernels rebuild in seconds.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tmap.h"
+
+namespace rab {
+
+constexpr int kMaxWorld = 16;
+
+// ------------------------------------------------------------------------------------------------
+// descriptor probe (tests)
+// ------------------------------------------------------------------------------------------------
+struct ProbeParams {
+  int mode;  // 0: SS K-major x K-major, 1: SS with MN-major B, 2: TS (A in TMEM) with MN-major B
+  int n;     // MMA N
+  int k;     // reduction length (multiple of 16, <= 128)
+  uint32_t idesc;
+  uint32_t a_lbo, a_sbo;
+  uint32_t b_lbo, b_sbo;
+  uint32_t b_kstep_bytes;  // start-address advance per K=16 step for an MN-major B operand
+};
+void launch_umma_probe(const CUtensorMap& map_a, const CUtensorMap& map_b, const ProbeParams& p,
+                       const void* a_raw, float* out, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// position maps: how local index i on ring rank r maps to a global token position.
+//   i <  seg_len : base0[r] + stride * i
+//   i >= seg_len : base1[r] + stride * (i - seg_len)
+// plain ring   : seg_len = n, base0 = r*n,  stride = 1
+// striped ring : seg_len = n, base0 = r,    stride = W
+// zig-zag      : seg_len = n/2, base0 = r*c, base1 = (2W-1-r)*c, stride = 1
+// ------------------------------------------------------------------------------------------------
+struct PosMap {
+  int stride;
+  int seg_len;
+  int base0[kMaxWorld];
+  int base1[kMaxWorld];
+};
+
+// ------------------------------------------------------------------------------------------------
+// fused ring flash-attention forward
+// ------------------------------------------------------------------------------------------------
+struct AttnFwdParams {
+  int batch, heads, kv_heads;
+  int n_q;      // local query rows
+  int n_k;      // keys per owner slot
+  int world;    // number of KV owner slots (ring size)
+  int rank;     // ring-local rank of this device
+  int causal;
+  int window;   // max (pos_q - pos_k), <= 0 disables
+  int is_bf16;
+  float scale;        // softmax scale
+  float softclamp;    // 0 disables, else tanh clamp value applied to scaled logits
+  PosMap pos;
+  int q_pos_offset;   // added to query positions (cross-attention causal alignment)
+  int hop_count;
+  int hop_owner[kMaxWorld];  // hop 0 is this rank
+  // outputs
+  void* o;       // [b, n_q, h, d] 16-bit
+  float* lse;    // [b, h, n_q] natural-log lse (+inf for rows with no visible key)
+  // key-padding bits: [world][batch][kmask_words] uint32 (bit set = keep), may be null
+  const uint32_t* kmask_bits;
+  int kmask_words;
+  // in-kernel K/V gather over NVLink
+  uint8_t* kv_local;                  // this rank's [world][2][b*hk][n_k][d] buffer
+  const uint8_t* kv_peer[kMaxWorld];  // same buffer on every ring peer (peer-mapped)
+  unsigned long long slot_bytes;      // bytes of one owner slot (K and V)
+  uint32_t* ready;                    // [world] arrival counters, zero before launch
+};
+
+template <int D>
+void launch_attn_fwd(const CUtensorMap& map_q, const CUtensorMap& map_kv, const AttnFwdParams& p, int num_sms,
+                     cudaStream_t stream);
+size_t attn_fwd_smem_bytes(int head_dim);
+
+// ------------------------------------------------------------------------------------------------
+// misc kernels (elementwise_sm100.cu)
+// ------------------------------------------------------------------------------------------------
+// k, v [b, n, hk, d] (arbitrary batch/seq/head strides, unit d stride) -> slot [2][b*hk][n][d]
+void launch_pack_kv(const void* k, const void* v, void* slot, int batch, int n, int kv_heads, int d,
+                    long long k_sb, long long k_sn, long long k_sh, long long v_sb, long long v_sn,
+                    long long v_sh, cudaStream_t stream);
+
+// cross-device barrier on symmetric signal pads: every rank bumps its epoch slot on every peer and
+// waits until all peers have bumped its own pad.
+struct BarrierParams {
+  int world;
+  int rank;
+  uint32_t epoch;
+  uint32_t* pads[kMaxWorld];  // pads[r] = signal pad living on rank r (peer-mapped), kMaxWorld words each
+};
+void launch_device_barrier(const BarrierParams& p, cudaStream_t stream);
+
+}  // namespace rab

@@ -1,0 +1,72 @@
+// Symmetric (peer-mapped) device memory for one NVSwitch box: every rank allocates the same-sized
+// region with cudaMalloc, exports a CUDA IPC handle, and maps every peer's region into its own address
+// space.  Kernels then address peer memory with ordinary global loads / TMA bulk copies over NVLink.
+//
+// The handle exchange itself (64 bytes per rank) rides on whatever torch.distributed backend is up;
+// this file is transport-agnostic.
+#include "symm.h"
+
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "tmap.h"
+
+namespace rab {
+
+namespace {
+std::mutex g_mu;
+std::unordered_map<void*, size_t> g_allocs;   // base -> bytes (owned by this process)
+std::unordered_map<void*, int> g_imports;     // imported peer base -> refcount
+}  // namespace
+
+void* symm_alloc(size_t bytes, unsigned char handle_out[kIpcHandleBytes]) {
+  void* base = nullptr;
+  // round to 2 MiB so the region is its own allocation (IPC handles map whole allocations)
+  const size_t rounded = (bytes + (2u << 20) - 1) & ~size_t((2u << 20) - 1);
+  cuda_check(cudaMalloc(&base, rounded), "symm_alloc cudaMalloc");
+  cuda_check(cudaMemset(base, 0, rounded), "symm_alloc memset");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, base);
+  if (e != cudaSuccess) {
+    // single-process use still works without IPC; report an all-zero handle
+    (void)cudaGetLastError();
+    std::memset(&h, 0, sizeof(h));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == kIpcHandleBytes, "IPC handle size");
+  std::memcpy(handle_out, &h, kIpcHandleBytes);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_allocs[base] = rounded;
+  return base;
+}
+
+void symm_free(void* base) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_allocs.erase(base);
+  }
+  cudaFree(base);
+}
+
+void* symm_open(const unsigned char handle[kIpcHandleBytes]) {
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, kIpcHandleBytes);
+  void* p = nullptr;
+  cuda_check(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "symm_open cudaIpcOpenMemHandle");
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_imports[p]++;
+  return p;
+}
+
+void symm_close(void* p) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_imports.find(p);
+    if (it == g_imports.end()) return;
+    if (--it->second > 0) return;
+    g_imports.erase(it);
+  }
+  cudaIpcCloseMemHandle(p);
+}
+
+}  // namespace rab

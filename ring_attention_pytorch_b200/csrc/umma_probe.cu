@@ -1,0 +1,134 @@
+// Descriptor validation kernel: runs ONE 128 x N x K tcgen05.mma tile with caller-supplied
+// descriptor parameters so every operand flavour the attention kernels rely on can be checked against
+// torch.matmul on the device (tests/test_umma_probe.py):
+//   mode 0: D = A * B^T   A[128][K] K-major (smem), B[N][K] K-major (smem)          (S = Q K^T)
+//   mode 1: D = A * B     A[128][K] K-major (smem), B[K][N] MN-major (smem)          (O = P V, SS form)
+//   mode 2: D = A * B     A[128][K] from TMEM (packed 16-bit, written with tcgen05.st), B[K][N] MN-major
+//                                                                                    (O = P V, TS form)
+// A and B tiles are brought in with 128B-swizzled TMA boxes of 64 elements x rows, exactly the way the
+// attention kernels stage Q/K/V.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace rab {
+
+struct ProbeSmem {
+  alignas(1024) uint8_t a[2][128 * 128];  // two 64-element-wide sub-tiles of up to 128 rows
+  alignas(1024) uint8_t b[2][128 * 128];
+  uint64_t bar_load;
+  uint64_t bar_mma;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  ProbeParams p, const uint16_t* __restrict__ a_raw, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  ProbeSmem& sm = *reinterpret_cast<ProbeSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x / 32;
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    mbar_init(&sm.bar_load, 1);
+    mbar_init(&sm.bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t d_tmem = tmem;           // columns [0, N)
+  const uint32_t a_tmem = tmem + 256;     // columns [256, 256 + K/2) for mode 2
+
+  if (tid == 0) {
+    // A: [128 rows][K] with K contiguous; one box per 64-wide k sub-tile.
+    uint32_t bytes = 0;
+    if (p.mode != 2) {
+      for (int s = 0; s < p.k / 64; ++s) {
+        tma_load_2d(sm.a[s], &map_a, &sm.bar_load, s * 64, 0);
+        bytes += 128 * 128;
+      }
+    }
+    if (p.mode == 0) {
+      // B: [N rows][K], box = 64 (k) x N rows
+      for (int s = 0; s < p.k / 64; ++s) {
+        tma_load_2d(sm.b[s], &map_b, &sm.bar_load, s * 64, 0);
+        bytes += p.n * 128;
+      }
+    } else {
+      // B: [K rows][N], box = 64 (n) x K rows, one per 64-wide n sub-tile
+      for (int s = 0; s < p.n / 64; ++s) {
+        tma_load_2d(sm.b[s], &map_b, &sm.bar_load, s * 64, 0);
+        bytes += p.k * 128;
+      }
+    }
+    mbar_expect_tx(&sm.bar_load, bytes);
+  }
+
+  if (p.mode == 2) {
+    // each thread writes its row of A (K 16-bit values = K/2 packed words) into TMEM
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(a_raw + (size_t)tid * p.k);
+    uint32_t regs[16];
+    for (int c = 0; c < p.k / 2; c += 16) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) regs[i] = row[c + i];
+      tmem_st16(a_tmem + (uint32_t(warp * 32) << 16) + c, regs);
+    }
+    tc_wait_st();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+
+  if (tid == 0) {
+    mbar_wait(&sm.bar_load, 0, 1);
+    tc_fence_after();
+    const uint64_t a_static = umma_smem_desc_hi_lo(p.a_lbo, p.a_sbo, UMMA_LAYOUT_SW128);
+    const uint64_t b_static = umma_smem_desc_hi_lo(p.b_lbo, p.b_sbo, UMMA_LAYOUT_SW128);
+    for (int kk = 0; kk < p.k / 16; ++kk) {
+      uint64_t bdesc;
+      if (p.mode == 0) {
+        bdesc = umma_desc(b_static, smem_u32(sm.b[kk / 4]) + (kk % 4) * 32);
+      } else {
+        bdesc = umma_desc(b_static, smem_u32(sm.b[0]) + kk * p.b_kstep_bytes);
+      }
+      if (p.mode == 2) {
+        umma_ts(d_tmem, a_tmem + kk * 8, bdesc, p.idesc, kk > 0);
+      } else {
+        const uint64_t adesc = umma_desc(a_static, smem_u32(sm.a[kk / 4]) + (kk % 4) * 32);
+        umma_ss(d_tmem, adesc, bdesc, p.idesc, kk > 0);
+      }
+    }
+    umma_commit(&sm.bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(&sm.bar_mma, 0, 2);
+  tc_fence_after();
+
+  // epilogue: thread t owns row t
+  for (int c = 0; c < p.n; c += 32) {
+    uint32_t regs[32];
+    tmem_ld32(d_tmem + (uint32_t(warp * 32) << 16) + c, regs);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[(size_t)tid * p.n + c + i] = __uint_as_float(regs[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+void launch_umma_probe(const CUtensorMap& map_a, const CUtensorMap& map_b, const ProbeParams& p,
+                       const void* a_raw, float* out, cudaStream_t stream) {
+  const int smem = sizeof(ProbeSmem) + 1024;
+  cuda_check(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+             "probe smem attr");
+  umma_probe_kernel<<<1, 128, smem, stream>>>(map_a, map_b, p, reinterpret_cast<const uint16_t*>(a_raw), out);
+  cuda_check(cudaGetLastError(), "probe launch");
+}
+
+}  // namespace rab

@@ -1,0 +1,98 @@
+"""Thin Python wrappers over the sm_100a kernels (``torch.ops.rab.*``).
+
+These are the building blocks the autograd ops in :mod:`ring_attention_pytorch_b200.ops.ring_cuda`
+compose; they are also what the GPU unit tests drive directly.  ``emulate_ring_forward`` runs a whole
+W-rank ring on ONE device by giving every emulated rank its own K/V gather buffer and pointing the
+"peer" addresses at the other ranks' buffers – the kernel cannot tell the difference, which lets the
+multi-hop fetch/ready-flag protocol be tested on a single GPU.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from ring_attention_pytorch_b200.ops import _ext
+from ring_attention_pytorch_b200.parallel.layout import PositionMap, make_position_map, ring_hop_owners
+
+
+def pack_key_mask_bits(mask: torch.Tensor) -> torch.Tensor:
+    """[world, b, n] bool (True = keep) -> [world, b, words] int32 bit-packed, words % 4 == 0."""
+    world, b, n = mask.shape
+    words = ((n + 127) // 128) * 4
+    padded = torch.zeros(world, b, words * 32, dtype=torch.bool, device=mask.device)
+    padded[..., :n] = mask
+    bits = padded.view(world, b, words, 32).to(torch.int64)
+    weights = (1 << torch.arange(32, device=mask.device, dtype=torch.int64))
+    packed = (bits * weights).sum(-1)
+    packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed)
+    return packed.to(torch.int32).contiguous()
+
+
+def alloc_kv_buffer(world: int, batch: int, kv_heads: int, n_k: int, d: int, dtype, device) -> torch.Tensor:
+    return torch.empty(world, 2, batch * kv_heads, n_k, d, dtype=dtype, device=device)
+
+
+def fused_attn_fwd(
+    q: torch.Tensor,
+    kv_buf: torch.Tensor,
+    peer_ptrs: Sequence[int],
+    ready: torch.Tensor,
+    kmask_bits: Optional[torch.Tensor],
+    *,
+    kv_heads: int,
+    rank: int,
+    pm: PositionMap,
+    causal: bool,
+    window: Optional[int],
+    scale: float,
+    softclamp: float = 0.0,
+    q_pos_offset: int = 0,
+    hop_owner: Optional[List[int]] = None,
+):
+    if hop_owner is None:
+        hop_owner = ring_hop_owners(pm, rank, causal, window)
+    return _ext.ops().attn_fwd(
+        q, kv_buf, list(peer_ptrs), ready, kmask_bits, kv_heads, rank, bool(causal), int(window or 0), float(scale),
+        float(softclamp), pm.stride, pm.seg_len, pm.base0, pm.base1, int(q_pos_offset), list(hop_owner))
+
+
+def emulate_ring_forward(
+    qs: Sequence[torch.Tensor],
+    ks: Sequence[torch.Tensor],
+    vs: Sequence[torch.Tensor],
+    *,
+    layout: str = "plain",
+    causal: bool = False,
+    window: Optional[int] = None,
+    softclamp: float = 0.0,
+    key_masks: Optional[Sequence[torch.Tensor]] = None,
+    scale: Optional[float] = None,
+):
+    """Run the fused forward for every rank of a W-rank ring on the current device.
+
+    qs/ks/vs: per-rank shards ``[b, n, h, d]`` / ``[b, n, hk, d]``.  Returns (outs, lses) lists.
+    """
+    ops = _ext.ops()
+    world = len(qs)
+    b, n, h, d = qs[0].shape
+    hk = ks[0].shape[2]
+    dev, dt = qs[0].device, qs[0].dtype
+    pm = make_position_map(layout, world, n)
+    scale = d ** -0.5 if scale is None else scale
+    bufs = [alloc_kv_buffer(world, b, hk, n, d, dt, dev) for _ in range(world)]
+    for r in range(world):
+        bufs[r].zero_()
+        ops.pack_kv(ks[r], vs[r], bufs[r][r])
+    kbits = None
+    if key_masks is not None:
+        kbits = pack_key_mask_bits(torch.stack(list(key_masks), 0))
+    outs, lses = [], []
+    for r in range(world):
+        ready = torch.zeros(world, dtype=torch.int32, device=dev)
+        peers = [bufs[o].data_ptr() for o in range(world)]
+        o, lse = fused_attn_fwd(qs[r].contiguous(), bufs[r], peers, ready, kbits, kv_heads=hk, rank=r, pm=pm,
+                                causal=causal, window=window, scale=scale, softclamp=softclamp)
+        outs.append(o)
+        lses.append(lse)
+    return outs, lses

@@ -1,0 +1,249 @@
+"""GPU bring-up checks, each case in its own subprocess with a timeout so a trap or hang in one kernel
+cannot take the rest of the (expensive) gpurun call down.
+
+    python tools/gpu_dev_check.py [--only probe,fwd,ring,perf] [--timeout 120]
+
+Writes gpurun_out/dev_check.log and prints a summary.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+# ----------------------------------------------------------------------------------------------
+# individual cases (run in a child process: `python tools/gpu_dev_check.py --case NAME`)
+# ----------------------------------------------------------------------------------------------
+def _idesc(M, N, a_mn, b_mn, bf16=1):
+    return (1 << 4) | (bf16 << 7) | (bf16 << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
+
+
+def case_probe(mode: int, variant: str = "base"):
+    import torch
+    from ring_attention_pytorch_b200.ops import _ext
+
+    ops = _ext.ops()
+    torch.manual_seed(0)
+    n, k = 128, 128
+    if variant == "n64":
+        n = 64
+    if variant == "k64":
+        k = 64
+    a = torch.randn(128, k, device="cuda", dtype=torch.bfloat16)
+    if mode == 0:
+        b = torch.randn(n, k, device="cuda", dtype=torch.bfloat16)
+        ref = a.float() @ b.float().t()
+        idesc = _idesc(128, n, 0, 0)
+        out = ops.umma_probe(a, b, 0, n, k, idesc, 16, 1024, 16, 1024, 0)
+    else:
+        b = torch.randn(k, n, device="cuda", dtype=torch.bfloat16)
+        ref = a.float() @ b.float()
+        idesc = _idesc(128, n, 0, 1)
+        lbo, sbo, kstep = 16384, 1024, 2048
+        if variant == "swap":
+            lbo, sbo = 1024, 16384
+        out = ops.umma_probe(a, b, mode, n, k, idesc, 16, 1024, lbo, sbo, kstep)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    rel = err / ref.abs().max().item()
+    return {"max_abs_err": err, "rel": rel, "ok": rel < 2e-2}
+
+
+def _ref_ring(qs, ks, vs, layout, causal, window, softclamp, key_masks):
+    import torch
+    from ring_attention_pytorch_b200.ops.oracle import attention_with_positions
+    from ring_attention_pytorch_b200.parallel.layout import make_position_map
+
+    world = len(qs)
+    n = qs[0].shape[1]
+    pm = make_position_map(layout, world, n)
+    k_all = torch.cat([k.float() for k in ks], 1)
+    v_all = torch.cat([v.float() for v in vs], 1)
+    k_pos = torch.cat([pm.positions(r, qs[0].device) for r in range(world)])
+    km = None if key_masks is None else torch.cat(list(key_masks), 1)
+    outs, lses = [], []
+    for r in range(world):
+        o, lse = attention_with_positions(qs[r].float(), k_all, v_all, pm.positions(r, qs[0].device), k_pos,
+                                          causal=causal, window=window, key_mask=km, softclamp_value=softclamp,
+                                          return_lse=True)
+        outs.append(o)
+        lses.append(lse)
+    return outs, lses
+
+
+def case_fwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=False, window=None, softclamp=0.0,
+             kmask=False, dtype="bf16", seed=0):
+    import torch
+    from ring_attention_pytorch_b200.ops.fused import emulate_ring_forward
+
+    hk = hk or h
+    torch.manual_seed(seed)
+    dt = torch.bfloat16 if dtype == "bf16" else torch.float16
+    qs = [torch.randn(b, n, h, d, device="cuda", dtype=dt) for _ in range(world)]
+    ks = [torch.randn(b, n, hk, d, device="cuda", dtype=dt) for _ in range(world)]
+    vs = [torch.randn(b, n, hk, d, device="cuda", dtype=dt) for _ in range(world)]
+    kms = None
+    if kmask:
+        kms = [torch.rand(b, n, device="cuda") > 0.3 for _ in range(world)]
+    outs, lses = emulate_ring_forward(qs, ks, vs, layout=layout, causal=causal, window=window, softclamp=softclamp,
+                                      key_masks=kms)
+    torch.cuda.synchronize()
+    routs, rlses = _ref_ring(qs, ks, vs, layout, causal, window, softclamp, kms)
+    err = max((o.float() - r).abs().max().item() for o, r in zip(outs, routs))
+    fin = [torch.isfinite(r) for r in rlses]
+    lerr = max(((l - r)[f]).abs().max().item() if f.any() else 0.0 for l, r, f in zip(lses, rlses, fin))
+    nan = any(torch.isnan(o.float()).any().item() for o in outs)
+    return {"max_abs_err": err, "lse_err": lerr, "nan": nan, "ok": (err < 3e-2) and (lerr < 2e-2) and not nan}
+
+
+def case_perf(n=16384, h=16, d=128, causal=True, iters=5, b=1, hk=None):
+    import torch
+    from ring_attention_pytorch_b200.ops import _ext
+    from ring_attention_pytorch_b200.ops.fused import alloc_kv_buffer, fused_attn_fwd
+    from ring_attention_pytorch_b200.parallel.layout import make_position_map
+
+    ops = _ext.ops()
+    hk = hk or h
+    dt = torch.bfloat16
+    q = torch.randn(b, n, h, d, device="cuda", dtype=dt)
+    k = torch.randn(b, n, hk, d, device="cuda", dtype=dt)
+    v = torch.randn(b, n, hk, d, device="cuda", dtype=dt)
+    pm = make_position_map("plain", 1, n)
+    buf = alloc_kv_buffer(1, b, hk, n, d, dt, "cuda")
+    ops.pack_kv(k, v, buf[0])
+    ready = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def run():
+        return fused_attn_fwd(q, buf, [0], ready, None, kv_heads=hk, rank=0, pm=pm, causal=causal, window=None,
+                              scale=d ** -0.5)
+
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[len(times) // 2]
+    flops = 4.0 * b * h * n * n * d * (0.5 if causal else 1.0)
+    res = {"ms": ms, "tflops": flops / ms / 1e9}
+    try:
+        from flash_attn import flash_attn_func
+
+        for _ in range(2):
+            flash_attn_func(q, k, v, causal=causal)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            flash_attn_func(q, k, v, causal=causal)
+        e1.record()
+        torch.cuda.synchronize()
+        res["flash_attn2_tflops"] = flops / (e0.elapsed_time(e1) / 3) / 1e9
+    except Exception as e:  # noqa: BLE001
+        res["flash_attn2_tflops"] = f"n/a: {type(e).__name__}"
+    res["ok"] = True
+    return res
+
+
+CASES = {
+    # descriptor probes
+    "probe_ss_kmajor": lambda: case_probe(0),
+    "probe_ss_kmajor_k64": lambda: case_probe(0, "k64"),
+    "probe_ss_mnmajor": lambda: case_probe(1),
+    "probe_ss_mnmajor_n64": lambda: case_probe(1, "n64"),
+    "probe_ss_mnmajor_swap": lambda: case_probe(1, "swap"),
+    "probe_ts_mnmajor": lambda: case_probe(2),
+    "probe_ts_mnmajor_n64": lambda: case_probe(2, "n64"),
+    # single-rank forward
+    "fwd_d128_n256": lambda: case_fwd(),
+    "fwd_d128_n128_h1": lambda: case_fwd(n=128, h=1),
+    "fwd_d128_causal_n512": lambda: case_fwd(n=512, causal=True),
+    "fwd_d128_n300_tail": lambda: case_fwd(n=300, b=2),
+    "fwd_d128_causal_n1000": lambda: case_fwd(n=1000, causal=True, h=4),
+    "fwd_d64_n512": lambda: case_fwd(n=512, d=64, h=4),
+    "fwd_d64_causal_n777": lambda: case_fwd(n=777, d=64, h=4, causal=True),
+    "fwd_gqa_causal": lambda: case_fwd(n=512, h=8, hk=2, causal=True),
+    "fwd_kmask": lambda: case_fwd(n=384, h=2, kmask=True, b=2),
+    "fwd_softclamp": lambda: case_fwd(n=384, h=2, softclamp=20.0),
+    "fwd_window": lambda: case_fwd(n=1024, h=2, causal=True, window=200),
+    "fwd_fp16": lambda: case_fwd(n=512, h=2, causal=True, dtype="fp16"),
+    "fwd_many_items": lambda: case_fwd(n=2048, h=16, b=2, causal=True),
+    # emulated rings (W ranks on one GPU)
+    "ring2_plain": lambda: case_fwd(world=2, n=256, h=2),
+    "ring2_plain_causal": lambda: case_fwd(world=2, n=256, h=2, causal=True),
+    "ring4_striped_causal": lambda: case_fwd(world=4, n=384, h=4, hk=2, layout="striped", causal=True),
+    "ring4_zigzag_causal": lambda: case_fwd(world=4, n=512, h=2, layout="zigzag", causal=True),
+    "ring4_plain_window": lambda: case_fwd(world=4, n=256, h=2, causal=True, window=300),
+    "ring3_kmask": lambda: case_fwd(world=3, n=200, h=2, kmask=True),
+    "ring8_striped_causal_big": lambda: case_fwd(world=8, n=1024, h=8, hk=2, layout="striped", causal=True),
+    # performance
+    "perf_causal_16k": lambda: case_perf(),
+    "perf_full_8k": lambda: case_perf(n=8192, causal=False),
+    "perf_causal_64k_h8": lambda: case_perf(n=65536, h=8, iters=3),
+    "perf_d64_causal_16k": lambda: case_perf(d=64, h=32),
+}
+
+GROUPS = {
+    "probe": [c for c in CASES if c.startswith("probe")],
+    "fwd": [c for c in CASES if c.startswith("fwd")],
+    "ring": [c for c in CASES if c.startswith("ring")],
+    "perf": [c for c in CASES if c.startswith("perf")],
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case")
+    ap.add_argument("--only", default="probe,fwd,ring,perf")
+    ap.add_argument("--timeout", type=int, default=150)
+    ap.add_argument("--log", default=os.path.join(ROOT, "gpurun_out", "dev_check.log"))
+    args = ap.parse_args()
+
+    if args.case:
+        res = CASES[args.case]()
+        print("RESULT " + json.dumps(res))
+        return
+
+    os.makedirs(os.path.dirname(args.log), exist_ok=True)
+    names = []
+    for g in args.only.split(","):
+        names += GROUPS.get(g, [g] if g in CASES else [])
+    summary = []
+    with open(args.log, "a") as log:
+        log.write(f"\n==== dev check {time.strftime('%F %T')} only={args.only}\n")
+        for name in names:
+            t0 = time.time()
+            try:
+                proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name], capture_output=True,
+                                      text=True, timeout=args.timeout)
+                out = proc.stdout + proc.stderr
+                line = [l for l in proc.stdout.splitlines() if l.startswith("RESULT ")]
+                status = line[-1][7:] if line else f"FAILED rc={proc.returncode}"
+            except subprocess.TimeoutExpired as e:
+                out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+                out += (e.stderr or b"").decode() if isinstance(e.stderr, bytes) else (e.stderr or "")
+                status = "TIMEOUT"
+            dt = time.time() - t0
+            msg = f"{name:32s} {dt:6.1f}s  {status}"
+            print(msg, flush=True)
+            summary.append(msg)
+            log.write(msg + "\n")
+            if not status.startswith("{") or '"ok": false' in status:
+                log.write("---- output tail\n" + out[-3000:] + "\n----\n")
+            log.flush()
+
+
+if __name__ == "__main__":
+    main()
