@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Headline benchmark: causal striped ring flash attention, forward + backward.
+
+Config (BASELINE.json config 1): total sequence 262144, 32 heads, head dim 128, bf16, batch 1, causal,
+striped layout, sequence sharded over the N GPUs of one box (STRONG scaling: total work is fixed).
+A "step" is one forward + one backward of the ring attention op on synthetic q/k/v (random-init).
+
+    python bench.py                      # N=1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference     # the unmodified reference from baseline/_ref (Triton + NCCL P2P)
+
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  The
+q/k/v shards (>= 268 MB each) are larger than the 126 MB L2, so no explicit flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seq-len", type=int, default=262144, help="TOTAL sequence length (all GPUs)")
+    ap.add_argument("--heads", type=int, default=32)
+    ap.add_argument("--kv-heads", type=int, default=None)
+    ap.add_argument("--dim-head", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fwd-only", action="store_true", help="diagnostic only (not a valid headline number)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+            return
+
+        def reader():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+
+        self.thread = threading.Thread(target=reader, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(smax) if smax else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def install_reference_shims():
+    """The reference refuses to import unless a distribution literally named ``triton-nightly`` exists
+    (reference triton_flash_attn.py:31-37).  Provide that *metadata only* next to the installed reference;
+    the reference's code is untouched."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "ring_attention_pytorch")):
+        raise RuntimeError("reference is not installed in baseline/_ref (see DESIGN.md)")
+    import triton
+
+    ver = triton.__version__.split("+")[0]
+    shim = os.path.join(ref, f"triton_nightly-{ver}.dist-info")
+    os.makedirs(shim, exist_ok=True)
+    meta = os.path.join(shim, "METADATA")
+    if not os.path.exists(meta):
+        with open(meta, "w") as f:
+            f.write(f"Metadata-Version: 2.1\nName: triton-nightly\nVersion: {ver}\n")
+    sys.path.insert(0, ref)
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (see module docstring)")
+        args.gpus = world
+
+    def unavailable(why: str):
+        if rank == 0:
+            print(json.dumps({"impl": args.impl, "unavailable": why.replace("\n", " ")[:300]}))
+        sys.exit(0)
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        if args.impl == "reference":
+            unavailable("no CUDA device")
+        raise SystemExit("bench.py needs a CUDA device")
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    S, H, D, B = args.seq_len, args.heads, args.dim_head, args.batch
+    HK = args.kv_heads or H
+    assert S % world == 0
+    n = S // world
+    ring = world > 1
+
+    if args.impl == "reference":
+        try:
+            install_reference_shims()
+            from ring_attention_pytorch.ring_flash_attention_cuda import ring_flash_attn_cuda as ref_attn
+        except BaseException as e:  # noqa: BLE001  (the reference calls exit() on import problems)
+            unavailable(f"reference import failed: {type(e).__name__}: {e}")
+
+        def attn(q, k, v):
+            return ref_attn(q, k, v, None, True, min(n, 1024), ring, ring, None, world)
+
+        launches = {"count": 0}
+    else:
+        from ring_attention_pytorch_b200.ops import ring_cuda
+
+        def attn(q, k, v):
+            return ring_cuda.ring_flash_attn_cuda(q, k, v, None, True, 1024, ring, ring, None, world)
+
+        launches = ring_cuda.LAUNCHES
+
+    torch.manual_seed(1234 + rank)
+    dt = torch.bfloat16
+    q = torch.randn(B, n, H, D, device=dev, dtype=dt, requires_grad=True)
+    k = torch.randn(B, n, HK, D, device=dev, dtype=dt, requires_grad=True)
+    v = torch.randn(B, n, HK, D, device=dev, dtype=dt, requires_grad=True)
+    w = torch.randn(B, n, H, D, device=dev, dtype=dt)  # fixed projection used as upstream gradient
+
+    def step():
+        out = attn(q, k, v)
+        if args.fwd_only:
+            return out
+        out.backward(w)
+        q.grad = k.grad = v.grad = None
+        return out
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    try:
+        for _ in range(args.warmup):
+            step()
+        sync()
+    except BaseException as e:  # noqa: BLE001
+        if args.impl == "reference":
+            unavailable(f"reference failed to run: {type(e).__name__}: {e}")
+        raise
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches_before = launches["count"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    n_launch = launches["count"] - launches_before
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    fwd_flops = 4.0 * B * H * float(S) * float(S) * D * 0.5
+    flops_per_step = fwd_flops * (1.0 if args.fwd_only else 3.5)
+    tflops = flops_per_step * args.steps / (ms * 1e-3) / 1e12
+    tokens_per_s = B * S * args.steps / (ms * 1e-3)
+
+    # ---------------- end-to-end: pinned host inputs -> device every step, loss read back ------------
+    e2e = None
+    if not args.no_e2e and not args.fwd_only:
+        hq = torch.randn(B, n, H, D, dtype=dt).pin_memory()
+        hk = torch.randn(B, n, HK, D, dtype=dt).pin_memory()
+        hv = torch.randn(B, n, HK, D, dtype=dt).pin_memory()
+        dq_, dk_, dv_ = (torch.empty_like(t_, device=dev) for t_ in (hq, hk, hv))
+
+        def e2e_step():
+            dq_.copy_(hq, non_blocking=True)
+            dk_.copy_(hk, non_blocking=True)
+            dv_.copy_(hv, non_blocking=True)
+            qq, kk, vv = (t_.detach().requires_grad_() for t_ in (dq_, dk_, dv_))
+            out = attn(qq, kk, vv)
+            loss = (out * w).sum(dtype=torch.float32)
+            loss.backward()
+            return float(loss.item())  # device -> host read of the step's result
+
+        e2e_step()
+        sync()
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        sync()
+        ems = e0.elapsed_time(e1)
+        t = torch.tensor([ems], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t.item())
+        h2d = (hq.numel() + hk.numel() + hv.numel()) * 2 * world
+        e2e = {
+            "value": flops_per_step * args.steps / (ems * 1e-3) / 1e12,
+            "unit": "TFLOP/s",
+            "ms_per_step": ems / args.steps,
+            "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": 4 * world,
+        }
+
+    if rank == 0:
+        line = {
+            "metric": "attention TFLOP/s (fwd+bwd, whole box, device-timed, max over ranks), causal striped ring",
+            "value": tflops,
+            "unit": "TFLOP/s",
+            "tokens_per_s": tokens_per_s,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "bf16",
+            "data": "synthetic q/k/v (random normal), random upstream gradient",
+            "impl": args.impl,
+            "config": {
+                "model": "causal striped ring flash-attn (BASELINE.json config 1)",
+                "global_batch": B,
+                "seq_len": S,
+                "heads": H,
+                "kv_heads": HK,
+                "dim_head": D,
+                "parallelism": f"cp{world}" + (" (striped ring)" if ring else ""),
+                "flops": "fwd 4*b*h*S^2*d*0.5, bwd 2.5x fwd (algorithmic 5-GEMM count)",
+                "l2": "inputs larger than L2 (no flush needed)",
+                "fwd_only": bool(args.fwd_only),
+            },
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": n_launch if args.impl == "ours" else 0,
+        }
+        print(json.dumps(line))
+
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,954 @@
+// Fused ring flash-attention backward for sm_100a: two warp-specialised tcgen05 kernels.
+//
+//   attn_bwd_dq_kernel   (Q-stationary)  per 128-row query tile, for every visible K/V tile:
+//        S = Q K^T (SS) -> P = exp2(S*c - lse)          dP = dO V^T (SS)
+//        dS = P o (dP - delta) * scale -> 16 bit in TMEM   dQ += dS K (TS, K as MN-major B)
+//   attn_bwd_dkdv_kernel (KV-stationary) per 128-key tile, for every query tile (64 rows) that can see it:
+//        S^T = K Q^T, dP^T = V dO^T (SS)                 P^T, dS^T -> 16 bit in TMEM
+//        dV += P^T dO, dK += dS^T Q (TS, dO / Q as MN-major B)
+//
+// Accumulators (dQ, or dK and dV) stay in TMEM for the whole ring: every rank finishes its own dQ, dK
+// and dV locally, so the backward needs neither atomics nor a cross-rank reduction.  The price is 7
+// instead of 5 GEMMs per tile pair; the reference (ring_flash_attention_cuda.py:211-351) runs a 5-GEMM
+// Triton kernel per hop but ships K, V, dK, dV around the ring in 16 bit, adds one extra dK/dV hop per
+// iteration and accumulates dQ through global read-modify-write.
+//
+// Both kernels run two independent "streams" (even / odd streamed tiles), each owning a TMEM region and a
+// 128-thread warpgroup; one MMA-issuing thread polls the two streams and issues whichever tcgen05.mma has
+// its dependencies satisfied, so a stream waiting on its warpgroup never blocks the tensor core.
+//
+// Inputs are the *gathered* ring buffers (see kernels.h); remote slots are published through ready flags.
+#include "attn_common.cuh"
+
+namespace rab {
+namespace {
+
+constexpr int NTHREADS = 384;
+constexpr int SUB128 = 128 * 128;  // 64-element-wide sub-tile, 128 rows
+constexpr int SUB64 = 64 * 128;    // 64-element-wide sub-tile, 64 rows
+
+__device__ __forceinline__ void wait_owner_ready(const AttnBwdParams& p, int owner, uint32_t& mask, int tag) {
+  if ((mask >> owner) & 1u) return;
+  if (p.ready != nullptr) {
+    spin_until_ge_gpu(p.ready + owner, p.ready_target, tag);
+    fence_proxy_async_global();
+  }
+  mask |= 1u << owner;
+}
+
+// =================================================================================================
+// dQ kernel
+// =================================================================================================
+template <int D>
+struct DqSmem {
+  static constexpr int NSUB = D / 64;
+  static constexpr int TILE = NSUB * SUB128;
+  alignas(1024) uint8_t q[TILE];
+  alignas(1024) uint8_t dout[TILE];
+  alignas(1024) uint8_t k[3][TILE];
+  alignas(1024) uint8_t v[2][TILE];
+  uint64_t qdo_full, qdo_empty;
+  uint64_t k_full[3], k_empty[3];
+  uint64_t v_full[2], v_empty[2];
+  uint64_t s_full[2], s_taken[2], dp_full[2], ds_ready[2];
+  uint64_t dq_done, epi_done;
+  uint32_t tmem_base;
+};
+
+struct DqItem {
+  int b, h, kvh, qt, row0;
+  int qlo, qhi;
+};
+
+__device__ __forceinline__ int dq_num_items(const AttnBwdParams& p) {
+  return p.batch * p.heads * ((p.n_q + 127) / 128);
+}
+
+__device__ __forceinline__ void dq_decode(const AttnBwdParams& p, int idx, DqItem& it) {
+  const int bh = p.batch * p.heads;
+  const int nqt = (p.n_q + 127) / 128;
+  it.qt = nqt - 1 - idx / bh;
+  const int r = idx % bh;
+  it.b = r / p.heads;
+  const int hh = r % p.heads;
+  const int groups = p.heads / p.kv_heads;
+  it.kvh = hh / groups;
+  it.h = (hh % groups) * p.kv_heads + it.kvh;
+  it.row0 = it.qt * 128;
+  pos_range(p.pos, p.rank, it.row0, min(it.row0 + 128, p.n_q) - 1, it.qlo, it.qhi);
+  it.qlo += p.q_pos_offset;
+  it.qhi += p.q_pos_offset;
+}
+
+struct KvTile {
+  int owner, kt;
+  bool part;
+};
+
+// Sequence of visible 128-key tiles of one dQ item (owners in hop order, tiles ascending).
+struct DqIter {
+  int s = 0, kt = 0;
+  __device__ __forceinline__ bool next(const AttnBwdParams& p, const DqItem& it, KvTile& t) {
+    const int nkt = (p.n_k + 127) / 128;
+    const MaskCfg mc{p.causal, p.window, p.kmask_bits != nullptr};
+    while (s < p.hop_count) {
+      const int o = p.hop_owner[s];
+      while (kt < nkt) {
+        const int k = kt++;
+        const int a = k * 128, bb = min(a + 128, p.n_k) - 1;
+        int klo, khi;
+        pos_range(p.pos, o, a, bb, klo, khi);
+        bool need, part;
+        classify_tile(mc, it.qlo, it.qhi, klo, khi, (a + 128) > p.n_k, need, part);
+        if (need) {
+          t.owner = o;
+          t.kt = k;
+          t.part = part;
+          return true;
+        }
+      }
+      kt = 0;
+      ++s;
+    }
+    return false;
+  }
+  // advance to the n-th next tile (n >= 1); returns false when the sequence ends first
+  __device__ __forceinline__ bool advance(const AttnBwdParams& p, const DqItem& it, KvTile& t, int n) {
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) ok = next(p, it, t);
+    return ok;
+  }
+};
+
+template <int D>
+__device__ __forceinline__ void dq_producer(DqSmem<D>& sm, const AttnBwdParams& p, const CUtensorMap* map_qd,
+                                            const CUtensorMap* map_kv) {
+  constexpr int NSUB = DqSmem<D>::NSUB;
+  constexpr uint32_t TILE = DqSmem<D>::TILE;
+  uint32_t n_item = 0, n_tile = 0;
+  uint32_t ready_mask = 1u << p.rank;
+  const int total = dq_num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
+    DqItem it;
+    dq_decode(p, idx, it);
+    mbar_wait(&sm.qdo_empty, (n_item & 1) ^ 1, 500);
+    mbar_expect_tx(&sm.qdo_full, 2 * TILE);
+#pragma unroll
+    for (int s = 0; s < NSUB; ++s) {
+      tma_load_4d(sm.q + s * SUB128, map_qd, &sm.qdo_full, s * 64, it.row0, it.b * p.heads + it.h, p.rank * 2);
+      tma_load_4d(sm.dout + s * SUB128, map_qd, &sm.qdo_full, s * 64, it.row0, it.b * p.heads + it.h,
+                  p.rank * 2 + 1);
+    }
+    DqIter iter;
+    KvTile t;
+    while (iter.next(p, it, t)) {
+      wait_owner_ready(p, t.owner, ready_mask, 501);
+      const uint32_t ks = n_tile % 3, kph = (n_tile / 3) & 1;
+      mbar_wait(&sm.k_empty[ks], kph ^ 1, 510 + ks);
+      mbar_expect_tx(&sm.k_full[ks], TILE);
+#pragma unroll
+      for (int s = 0; s < NSUB; ++s)
+        tma_load_4d(sm.k[ks] + s * SUB128, map_kv, &sm.k_full[ks], s * 64, t.kt * 128, it.b * p.kv_heads + it.kvh,
+                    t.owner * 2);
+      const uint32_t vs = n_tile % 2, vph = (n_tile / 2) & 1;
+      mbar_wait(&sm.v_empty[vs], vph ^ 1, 520 + vs);
+      mbar_expect_tx(&sm.v_full[vs], TILE);
+#pragma unroll
+      for (int s = 0; s < NSUB; ++s)
+        tma_load_4d(sm.v[vs] + s * SUB128, map_kv, &sm.v_full[vs], s * 64, t.kt * 128, it.b * p.kv_heads + it.kvh,
+                    t.owner * 2 + 1);
+      n_tile++;
+    }
+  }
+}
+
+template <int D, bool BF16>
+__device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem) {
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0, BF16 ? 1 : 0);   // S, dP : N = 128 keys
+  constexpr uint32_t idesc_dq = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);    // dQ    : N = D, B MN-major
+  constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
+  constexpr uint64_t mnmaj = umma_smem_desc_hi_lo(SUB128, 1024, UMMA_LAYOUT_SW128);
+  const uint32_t x_tm[2] = {tmem + 0, tmem + 128};
+  const uint32_t dq_tm = tmem + 256;
+
+  uint32_t n_item = 0, tile_base = 0;
+  uint32_t cnt[2] = {0, 0};  // tiles completed per stream (global) -> barrier parities
+  const int total = dq_num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
+    DqItem it;
+    dq_decode(p, idx, it);
+    mbar_wait(&sm.qdo_full, n_item & 1, 600);
+    tc_fence_after();
+
+    DqIter iters[2];
+    KvTile tl[2];
+    int state[2];  // 0: need S, 1: need dP, 2: need dQ, 3: done
+    uint32_t jj[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      jj[w] = w;
+      state[w] = iters[w].advance(p, it, tl[w], w + 1) ? 0 : 3;
+    }
+    bool dq_started = false;
+    uint32_t ntiles = 0;
+    const uint32_t qa = smem_u32(sm.q), da = smem_u32(sm.dout);
+    while (state[0] != 3 || state[1] != 3) {
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        if (state[w] == 3) continue;
+        const uint32_t g = tile_base + jj[w];
+        const uint32_t ks = g % 3, kph = (g / 3) & 1, vs = g % 2, vph = (g / 2) & 1;
+        if (state[w] == 0) {
+          if (!mbar_test_wait(&sm.k_full[ks], kph)) continue;
+          tc_fence_after();
+          const uint32_t ka = smem_u32(sm.k[ks]);
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
+            umma_ss(x_tm[w], umma_desc(kmaj, qa + off), umma_desc(kmaj, ka + off), idesc_s, kk > 0);
+          }
+          umma_commit(&sm.s_full[w]);
+          state[w] = 1;
+        } else if (state[w] == 1) {
+          if (!mbar_test_wait(&sm.v_full[vs], vph)) continue;
+          if (!mbar_test_wait(&sm.s_taken[w], cnt[w] & 1)) continue;
+          tc_fence_after();
+          const uint32_t va = smem_u32(sm.v[vs]);
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
+            umma_ss(x_tm[w], umma_desc(kmaj, da + off), umma_desc(kmaj, va + off), idesc_s, kk > 0);
+          }
+          umma_commit(&sm.dp_full[w]);
+          umma_commit(&sm.v_empty[vs]);
+          state[w] = 2;
+        } else {
+          if (!mbar_test_wait(&sm.ds_ready[w], cnt[w] & 1)) continue;
+          if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 610);
+          tc_fence_after();
+          const uint32_t ka = smem_u32(sm.k[ks]);
+#pragma unroll
+          for (int kk = 0; kk < 128 / 16; ++kk) {
+            umma_ts(dq_tm, x_tm[w] + kk * 8, umma_desc(mnmaj, ka + kk * 2048), idesc_dq,
+                    (dq_started || kk > 0) ? 1u : 0u);
+          }
+          dq_started = true;
+          umma_commit(&sm.k_empty[ks]);
+          cnt[w]++;
+          ntiles++;
+          jj[w] += 2;
+          state[w] = iters[w].advance(p, it, tl[w], 2) ? 0 : 3;
+        }
+      }
+    }
+    if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 611);
+    umma_commit(&sm.dq_done);
+    umma_commit(&sm.qdo_empty);
+    tile_base += ntiles;
+  }
+}
+
+template <int D, bool BF16, int W>
+__device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem) {
+  const int wg_tid = threadIdx.x - (128 + 128 * W);
+  const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
+  const uint32_t x_tm = tmem + W * 128 + lane_off;
+  const uint32_t dq_tm = tmem + 256 + lane_off;
+  uint32_t cnt = 0, n_item = 0;
+
+  const bool clamp = p.softclamp > 0.f;
+  const float mul = clamp ? 1.f : p.scale * kLog2e;
+  const float pre = clamp ? p.scale / p.softclamp : 0.f;
+  const float post = clamp ? p.softclamp * kLog2e : 0.f;
+
+  const int total = dq_num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
+    DqItem it;
+    dq_decode(p, idx, it);
+    const int grow = it.row0 + wg_tid;
+    const bool row_ok = grow < p.n_q;
+    const int pos_q = pos_of(p.pos, p.rank, min(grow, p.n_q - 1)) + p.q_pos_offset;
+    const size_t stat_row = ((size_t)(p.rank * 2) * p.batch * p.heads + (size_t)it.b * p.heads + it.h) * p.n_pad;
+    float lse2 = INFINITY, delta = 0.f;
+    if (row_ok) {
+      lse2 = p.stat[stat_row + grow];
+      delta = p.stat[stat_row + (size_t)p.batch * p.heads * p.n_pad + grow];
+    }
+
+    DqIter iter;
+    KvTile t;
+    bool ok = iter.advance(p, it, t, W + 1);
+    while (ok) {
+      mbar_wait(&sm.s_full[W], cnt & 1, 700 + W);
+      tc_fence_after();
+      uint32_t sr[128];
+      tmem_ld32(x_tm + 0, sr + 0);
+      tmem_ld32(x_tm + 32, sr + 32);
+      tmem_ld32(x_tm + 64, sr + 64);
+      tmem_ld32(x_tm + 96, sr + 96);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&sm.s_taken[W]);
+
+      if (t.part) {
+        const int c0 = t.kt * 128;
+        const int split = p.pos.seg_len - c0;
+        const int a0 = p.pos.base0[t.owner] + p.pos.stride * c0;
+        const int a1 = p.pos.base1[t.owner] + p.pos.stride * (c0 - p.pos.seg_len);
+        uint32_t mb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (p.kmask_bits != nullptr) {
+          const uint32_t* w = p.kmask_bits + ((size_t)t.owner * p.batch + it.b) * p.kmask_words + (size_t)t.kt * 4;
+          mb[0] = w[0]; mb[1] = w[1]; mb[2] = w[2]; mb[3] = w[3];
+        }
+        const int ncols = p.n_k - c0;
+#pragma unroll
+        for (int j = 0; j < 128; ++j) {
+          const int pk = (j < split ? a0 : a1) + p.pos.stride * j;
+          bool keep = (j < ncols) && ((mb[j >> 5] >> (j & 31)) & 1u);
+          if (p.causal) {
+            keep = keep && (pk <= pos_q);
+            if (p.window > 0) keep = keep && (pos_q - pk <= p.window);
+          }
+          if (!keep) sr[j] = 0xff800000u;
+        }
+      }
+
+      mbar_wait(&sm.dp_full[W], cnt & 1, 710 + W);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t dp[32];
+        tmem_ld32(x_tm + c * 32, dp);
+        tc_wait_ld();
+        uint32_t w16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float ds2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float s = __uint_as_float(sr[c * 32 + 2 * i + e]);
+            float pj, chain = p.scale;
+            if (clamp) {
+              const float th = fast_tanh(s * pre);
+              pj = fast_exp2(fmaf(th, post, -lse2));
+              chain *= (1.f - th * th);
+            } else {
+              pj = fast_exp2(fmaf(s, mul, -lse2));
+            }
+            if (s == -INFINITY) pj = 0.f;
+            ds2[e] = pj * (__uint_as_float(dp[2 * i + e]) - delta) * chain;
+          }
+          w16[i] = BF16 ? pack_bf16x2(ds2[0], ds2[1]) : pack_f16x2(ds2[0], ds2[1]);
+        }
+        tmem_st16(x_tm + c * 16, w16);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&sm.ds_ready[W]);
+      cnt++;
+      ok = iter.advance(p, it, t, 2);
+    }
+
+    // epilogue: warpgroup W converts columns [W*D/2, (W+1)*D/2) of dQ
+    mbar_wait(&sm.dq_done, n_item & 1, 720 + W);
+    tc_fence_after();
+    {
+      // the item may have had no visible tile at all: dQ is then zero and TMEM holds stale data
+      DqIter probe;
+      KvTile tt;
+      const bool any = probe.next(p, it, tt);
+      uint16_t* drow = reinterpret_cast<uint16_t*>(p.dq) +
+                       (((size_t)it.b * p.n_q + (row_ok ? grow : 0)) * p.heads + it.h) * D + W * (D / 2);
+#pragma unroll
+      for (int c = 0; c < D / 2; c += 32) {
+        uint32_t acc[32];
+        if (any) {
+          tmem_ld32(dq_tm + W * (D / 2) + c, acc);
+          tc_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = 0u;
+        }
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = __uint_as_float(acc[2 * i]), bq = __uint_as_float(acc[2 * i + 1]);
+          w[i] = BF16 ? pack_bf16x2(a, bq) : pack_f16x2(a, bq);
+        }
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(drow + c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(&sm.epi_done);
+  }
+}
+
+template <int D, bool BF16>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_constant__ CUtensorMap map_kv,
+                   const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  DqSmem<D>& sm = *reinterpret_cast<DqSmem<D>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x / 32;
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.qdo_full, 1);
+    mbar_init(&sm.qdo_empty, 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&sm.k_full[i], 1);
+      mbar_init(&sm.k_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.v_full[i], 1);
+      mbar_init(&sm.v_empty[i], 1);
+      mbar_init(&sm.s_full[i], 1);
+      mbar_init(&sm.s_taken[i], 128);
+      mbar_init(&sm.dp_full[i], 1);
+      mbar_init(&sm.ds_ready[i], 128);
+    }
+    mbar_init(&sm.dq_done, 1);
+    mbar_init(&sm.epi_done, 256);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  if (warp < 4) {
+    setmaxnreg_dec<72>();
+    if (lane_id() == 0) {
+      if (warp == 0) dq_producer<D>(sm, p, &map_qd, &map_kv);
+      if (warp == 1) dq_mma<D, BF16>(sm, p, tmem);
+    }
+  } else {
+    setmaxnreg_inc<216>();
+    if (warp < 8) {
+      dq_softmax<D, BF16, 0>(sm, p, tmem);
+    } else {
+      dq_softmax<D, BF16, 1>(sm, p, tmem);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// =================================================================================================
+// dK/dV kernel
+// =================================================================================================
+constexpr int QSTAGES = 3;
+
+template <int D>
+struct DkvSmem {
+  static constexpr int NSUB = D / 64;
+  static constexpr int KV_TILE = NSUB * SUB128;  // 128 keys
+  static constexpr int Q_TILE = NSUB * SUB64;    // 64 queries
+  alignas(1024) uint8_t k[KV_TILE];
+  alignas(1024) uint8_t v[KV_TILE];
+  alignas(1024) uint8_t q[QSTAGES][Q_TILE];
+  alignas(1024) uint8_t dout[QSTAGES][Q_TILE];
+  alignas(16) float lse2[QSTAGES][64];
+  alignas(16) float delta[QSTAGES][64];
+  uint64_t kv_full, kv_empty;
+  uint64_t qd_full[QSTAGES], qd_empty[QSTAGES];
+  uint64_t sdp_full[2], pds_ready[2];
+  uint64_t acc_done, epi_done;
+  uint32_t tmem_base;
+};
+
+struct DkvItem {
+  int b, kvh, kt, key0;
+  int klo, khi;
+  bool k_tail;
+};
+
+__device__ __forceinline__ int dkv_num_items(const AttnBwdParams& p) {
+  return p.batch * p.kv_heads * ((p.n_k + 127) / 128);
+}
+
+__device__ __forceinline__ void dkv_decode(const AttnBwdParams& p, int idx, DkvItem& it) {
+  const int bh = p.batch * p.kv_heads;
+  it.kt = idx / bh;  // early key tiles are visible to the most queries under causal masking: heaviest first
+  const int r = idx % bh;
+  it.b = r / p.kv_heads;
+  it.kvh = r % p.kv_heads;
+  it.key0 = it.kt * 128;
+  pos_range(p.pos, p.rank, it.key0, min(it.key0 + 128, p.n_k) - 1, it.klo, it.khi);
+  it.k_tail = (it.key0 + 128) > p.n_k;
+}
+
+struct QTile {
+  int g, owner, qt;  // query head = g * kv_heads + kvh, rows [qt*64, qt*64+64) of `owner`
+  bool part;
+};
+
+// Sequence of visible 64-query tiles of one dK/dV item: group heads x owners (hop order) x tiles.
+struct DkvIter {
+  int g = 0, s = 0, qt = 0;
+  __device__ __forceinline__ bool next(const AttnBwdParams& p, const DkvItem& it, QTile& t) {
+    const int nqt = (p.n_q + 63) / 64;
+    const int groups = p.heads / p.kv_heads;
+    const MaskCfg mc{p.causal, p.window, p.kmask_bits != nullptr};
+    while (g < groups) {
+      while (s < p.hop_count) {
+        const int o = p.hop_owner[s];
+        while (qt < nqt) {
+          const int i = qt++;
+          const int a = i * 64, bb = min(a + 64, p.n_q) - 1;
+          int qlo, qhi;
+          pos_range(p.pos, o, a, bb, qlo, qhi);
+          qlo += p.q_pos_offset;
+          qhi += p.q_pos_offset;
+          bool need, part;
+          classify_tile(mc, qlo, qhi, it.klo, it.khi, it.k_tail || (a + 64) > p.n_q, need, part);
+          if (need) {
+            t.g = g;
+            t.owner = o;
+            t.qt = i;
+            t.part = part;
+            return true;
+          }
+        }
+        qt = 0;
+        ++s;
+      }
+      s = 0;
+      ++g;
+    }
+    return false;
+  }
+  __device__ __forceinline__ bool advance(const AttnBwdParams& p, const DkvItem& it, QTile& t, int n) {
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) ok = next(p, it, t);
+    return ok;
+  }
+};
+
+template <int D>
+__device__ __forceinline__ void dkv_producer(DkvSmem<D>& sm, const AttnBwdParams& p, const CUtensorMap* map_qd64,
+                                             const CUtensorMap* map_kv) {
+  constexpr int NSUB = DkvSmem<D>::NSUB;
+  constexpr uint32_t KV_TILE = DkvSmem<D>::KV_TILE, Q_TILE = DkvSmem<D>::Q_TILE;
+  uint32_t n_item = 0, n_tile = 0;
+  uint32_t ready_mask = 1u << p.rank;
+  const int total = dkv_num_items(p);
+  const size_t stat_half = (size_t)p.batch * p.heads * p.n_pad;
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
+    DkvItem it;
+    dkv_decode(p, idx, it);
+    mbar_wait(&sm.kv_empty, (n_item & 1) ^ 1, 800);
+    mbar_expect_tx(&sm.kv_full, 2 * KV_TILE);
+#pragma unroll
+    for (int s = 0; s < NSUB; ++s) {
+      tma_load_4d(sm.k + s * SUB128, map_kv, &sm.kv_full, s * 64, it.key0, it.b * p.kv_heads + it.kvh, p.rank * 2);
+      tma_load_4d(sm.v + s * SUB128, map_kv, &sm.kv_full, s * 64, it.key0, it.b * p.kv_heads + it.kvh,
+                  p.rank * 2 + 1);
+    }
+    DkvIter iter;
+    QTile t;
+    while (iter.next(p, it, t)) {
+      wait_owner_ready(p, t.owner, ready_mask, 801);
+      const uint32_t st = n_tile % QSTAGES, ph = (n_tile / QSTAGES) & 1;
+      const int h = t.g * p.kv_heads + it.kvh;
+      const int bh = it.b * p.heads + h;
+      mbar_wait(&sm.qd_empty[st], ph ^ 1, 810 + st);
+      mbar_expect_tx(&sm.qd_full[st], 2 * Q_TILE + 2 * 64 * 4);
+#pragma unroll
+      for (int s = 0; s < NSUB; ++s) {
+        tma_load_4d(sm.q[st] + s * SUB64, map_qd64, &sm.qd_full[st], s * 64, t.qt * 64, bh, t.owner * 2);
+        tma_load_4d(sm.dout[st] + s * SUB64, map_qd64, &sm.qd_full[st], s * 64, t.qt * 64, bh, t.owner * 2 + 1);
+      }
+      const float* srow = p.stat + ((size_t)(t.owner * 2) * p.batch * p.heads + bh) * p.n_pad + (size_t)t.qt * 64;
+      bulk_load_1d(sm.lse2[st], srow, 64 * 4, &sm.qd_full[st]);
+      bulk_load_1d(sm.delta[st], srow + stat_half, 64 * 4, &sm.qd_full[st]);
+      n_tile++;
+    }
+  }
+}
+
+template <int D, bool BF16>
+__device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem) {
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);   // S^T, dP^T : N = 64 queries
+  constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);  // dV, dK    : N = D, B MN-major
+  constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
+  constexpr uint64_t mnmaj64 = umma_smem_desc_hi_lo(SUB64, 1024, UMMA_LAYOUT_SW128);
+  // TMEM: stream w: S^T at w*128 (P^T aliases its first 32 columns), dP^T at w*128+64 (dS^T aliases it)
+  const uint32_t st_tm[2] = {tmem + 0, tmem + 128};
+  const uint32_t dpt_tm[2] = {tmem + 64, tmem + 192};
+  const uint32_t dk_tm = tmem + 256, dv_tm = tmem + 256 + D;
+
+  uint32_t n_item = 0, tile_base = 0;
+  uint32_t cnt[2] = {0, 0};
+  const int total = dkv_num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
+    DkvItem it;
+    dkv_decode(p, idx, it);
+    mbar_wait(&sm.kv_full, n_item & 1, 900);
+    tc_fence_after();
+
+    DkvIter iters[2];
+    QTile tl[2];
+    int state[2];  // 0: need S^T/dP^T, 1: need dV/dK, 3: done
+    uint32_t jj[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      jj[w] = w;
+      state[w] = iters[w].advance(p, it, tl[w], w + 1) ? 0 : 3;
+    }
+    bool acc_started = false;
+    uint32_t ntiles = 0;
+    const uint32_t ka = smem_u32(sm.k), va = smem_u32(sm.v);
+    while (state[0] != 3 || state[1] != 3) {
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        if (state[w] == 3) continue;
+        const uint32_t g = tile_base + jj[w];
+        const uint32_t st = g % QSTAGES, ph = (g / QSTAGES) & 1;
+        const uint32_t qa = smem_u32(sm.q[st]), da = smem_u32(sm.dout[st]);
+        if (state[w] == 0) {
+          if (!mbar_test_wait(&sm.qd_full[st], ph)) continue;
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+            const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+            umma_ss(st_tm[w], umma_desc(kmaj, ka + offk), umma_desc(kmaj, qa + offq), idesc_s, kk > 0);
+          }
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+            const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+            umma_ss(dpt_tm[w], umma_desc(kmaj, va + offk), umma_desc(kmaj, da + offq), idesc_s, kk > 0);
+          }
+          umma_commit(&sm.sdp_full[w]);
+          state[w] = 1;
+        } else {
+          if (!mbar_test_wait(&sm.pds_ready[w], cnt[w] & 1)) continue;
+          if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 910);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 64 / 16; ++kk) {
+            umma_ts(dv_tm, st_tm[w] + kk * 8, umma_desc(mnmaj64, da + kk * 2048), idesc_acc,
+                    (acc_started || kk > 0) ? 1u : 0u);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 64 / 16; ++kk) {
+            umma_ts(dk_tm, dpt_tm[w] + kk * 8, umma_desc(mnmaj64, qa + kk * 2048), idesc_acc,
+                    (acc_started || kk > 0) ? 1u : 0u);
+          }
+          acc_started = true;
+          umma_commit(&sm.qd_empty[st]);
+          cnt[w]++;
+          ntiles++;
+          jj[w] += 2;
+          state[w] = iters[w].advance(p, it, tl[w], 2) ? 0 : 3;
+        }
+      }
+    }
+    if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 911);
+    umma_commit(&sm.acc_done);
+    umma_commit(&sm.kv_empty);
+    tile_base += ntiles;
+  }
+}
+
+template <int D, bool BF16, int W>
+__device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem) {
+  const int wg_tid = threadIdx.x - (128 + 128 * W);
+  const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
+  const uint32_t st_tm = tmem + W * 128 + lane_off;
+  const uint32_t dpt_tm = tmem + W * 128 + 64 + lane_off;
+  uint32_t cnt = 0, n_item = 0, tile_base = 0;
+
+  const bool clamp = p.softclamp > 0.f;
+  const float mul = clamp ? 1.f : p.scale * kLog2e;
+  const float pre = clamp ? p.scale / p.softclamp : 0.f;
+  const float post = clamp ? p.softclamp * kLog2e : 0.f;
+
+  const int total = dkv_num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
+    DkvItem it;
+    dkv_decode(p, idx, it);
+    const int key = it.key0 + wg_tid;
+    bool key_ok = key < p.n_k;
+    const int pos_k = pos_of(p.pos, p.rank, min(key, p.n_k - 1));
+    if (key_ok && p.kmask_bits != nullptr) {
+      const uint32_t wbits = p.kmask_bits[((size_t)p.rank * p.batch + it.b) * p.kmask_words + (key >> 5)];
+      key_ok = (wbits >> (key & 31)) & 1u;
+    }
+
+    DkvIter iter;
+    QTile t;
+    uint32_t jj = W;
+    uint32_t ntiles_w = 0;
+    bool ok = iter.advance(p, it, t, W + 1);
+    while (ok) {
+      const uint32_t stg = (tile_base + jj) % QSTAGES;
+      mbar_wait(&sm.sdp_full[W], cnt & 1, 1000 + W);
+      tc_fence_after();
+      uint32_t sr[64], dp[64];
+      tmem_ld32(st_tm + 0, sr + 0);
+      tmem_ld32(st_tm + 32, sr + 32);
+      tmem_ld32(dpt_tm + 0, dp + 0);
+      tmem_ld32(dpt_tm + 32, dp + 32);
+      tc_wait_ld();
+
+      const int c0 = t.qt * 64;
+      const int split = p.pos.seg_len - c0;
+      const int a0 = p.pos.base0[t.owner] + p.pos.stride * c0 + p.q_pos_offset;
+      const int a1 = p.pos.base1[t.owner] + p.pos.stride * (c0 - p.pos.seg_len) + p.q_pos_offset;
+      const int ncols = p.n_q - c0;
+      const float4* l4 = reinterpret_cast<const float4*>(sm.lse2[stg]);
+      const float4* d4 = reinterpret_cast<const float4*>(sm.delta[stg]);
+      uint32_t pw[32], dw[32];
+#pragma unroll
+      for (int q4 = 0; q4 < 16; ++q4) {
+        const float4 lv = l4[q4];
+        const float4 dv = d4[q4];
+        const float ls[4] = {lv.x, lv.y, lv.z, lv.w};
+        const float dl[4] = {dv.x, dv.y, dv.z, dv.w};
+        float pp[4], dd[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = q4 * 4 + e;
+          const float s = __uint_as_float(sr[j]);
+          float pj, chain = p.scale;
+          if (clamp) {
+            const float th = fast_tanh(s * pre);
+            pj = fast_exp2(fmaf(th, post, -ls[e]));
+            chain *= (1.f - th * th);
+          } else {
+            pj = fast_exp2(fmaf(s, mul, -ls[e]));
+          }
+          bool keep = key_ok;
+          if (t.part) {
+            const int pq = (j < split ? a0 : a1) + p.pos.stride * j;
+            keep = keep && (j < ncols);
+            if (p.causal) {
+              keep = keep && (pos_k <= pq);
+              if (p.window > 0) keep = keep && (pq - pos_k <= p.window);
+            }
+          }
+          if (!keep) pj = 0.f;
+          pp[e] = pj;
+          dd[e] = pj * (__uint_as_float(dp[j]) - dl[e]) * chain;
+        }
+        pw[q4 * 2] = BF16 ? pack_bf16x2(pp[0], pp[1]) : pack_f16x2(pp[0], pp[1]);
+        pw[q4 * 2 + 1] = BF16 ? pack_bf16x2(pp[2], pp[3]) : pack_f16x2(pp[2], pp[3]);
+        dw[q4 * 2] = BF16 ? pack_bf16x2(dd[0], dd[1]) : pack_f16x2(dd[0], dd[1]);
+        dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(dd[2], dd[3]) : pack_f16x2(dd[2], dd[3]);
+      }
+      tmem_st32(st_tm, pw);
+      tmem_st32(dpt_tm, dw);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&sm.pds_ready[W]);
+      cnt++;
+      ntiles_w++;
+      jj += 2;
+      ok = iter.advance(p, it, t, 2);
+    }
+    // both warpgroups need the item's total tile count to keep the stage ring in step
+    {
+      DkvIter count_iter;
+      QTile tt;
+      uint32_t n = 0;
+      while (count_iter.next(p, it, tt)) ++n;
+      tile_base += n;
+    }
+
+    // epilogue: warpgroup 0 writes dK, warpgroup 1 writes dV
+    mbar_wait(&sm.acc_done, n_item & 1, 1010 + W);
+    tc_fence_after();
+    {
+      DkvIter probe;
+      QTile tt;
+      const bool any = probe.next(p, it, tt);
+      const uint32_t acc_tm = tmem + 256 + (W == 0 ? 0 : D) + lane_off;
+      const bool row_ok = key < p.n_k;
+      uint16_t* out = reinterpret_cast<uint16_t*>(W == 0 ? p.dk : p.dv) +
+                      (((size_t)it.b * p.n_k + (row_ok ? key : 0)) * p.kv_heads + it.kvh) * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 32) {
+        uint32_t acc[32];
+        if (any) {
+          tmem_ld32(acc_tm + c, acc);
+          tc_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = 0u;
+        }
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = __uint_as_float(acc[2 * i]), bq = __uint_as_float(acc[2 * i + 1]);
+          w[i] = BF16 ? pack_bf16x2(a, bq) : pack_f16x2(a, bq);
+        }
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(out + c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(&sm.epi_done);
+  }
+}
+
+template <int D, bool BF16>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_constant__ CUtensorMap map_kv,
+                     const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  DkvSmem<D>& sm = *reinterpret_cast<DkvSmem<D>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x / 32;
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.kv_full, 1);
+    mbar_init(&sm.kv_empty, 1);
+    for (int i = 0; i < QSTAGES; ++i) {
+      mbar_init(&sm.qd_full[i], 1);
+      mbar_init(&sm.qd_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.sdp_full[i], 1);
+      mbar_init(&sm.pds_ready[i], 128);
+    }
+    mbar_init(&sm.acc_done, 1);
+    mbar_init(&sm.epi_done, 256);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  if (warp < 4) {
+    setmaxnreg_dec<72>();
+    if (lane_id() == 0) {
+      if (warp == 0) dkv_producer<D>(sm, p, &map_qd64, &map_kv);
+      if (warp == 1) dkv_mma<D, BF16>(sm, p, tmem);
+    }
+  } else {
+    setmaxnreg_inc<216>();
+    if (warp < 8) {
+      dkv_softmax<D, BF16, 0>(sm, p, tmem);
+    } else {
+      dkv_softmax<D, BF16, 1>(sm, p, tmem);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// =================================================================================================
+// prep: delta = rowsum(o * do), lse -> log2 domain, q / do -> head-major slot
+// =================================================================================================
+template <bool BF16>
+__global__ void bwd_prep_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ o,
+                                const uint16_t* __restrict__ dout, const float* __restrict__ lse,
+                                uint16_t* __restrict__ qdo_slot, float* __restrict__ stat_slot, int batch, int n,
+                                int heads, int d, int n_pad) {
+  const int vec_per_row = d / 8;  // 8 or 16 lanes per row
+  const long long rows = (long long)batch * n * heads;
+  const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long row = gid / vec_per_row;
+  const int c = gid % vec_per_row;
+  float part = 0.f;
+  long long out_row = 0;
+  int hh = 0, i = 0, b = 0;
+  const bool active = row < rows;
+  if (active) {
+    hh = row % heads;
+    i = (row / heads) % n;
+    b = row / ((long long)heads * n);
+    out_row = ((long long)b * heads + hh) * n + i;
+    const uint4 qv = reinterpret_cast<const uint4*>(q + row * d)[c];
+    const uint4 ov = reinterpret_cast<const uint4*>(o + row * d)[c];
+    const uint4 dv = reinterpret_cast<const uint4*>(dout + row * d)[c];
+    reinterpret_cast<uint4*>(qdo_slot + out_row * d)[c] = qv;
+    reinterpret_cast<uint4*>(qdo_slot + (rows + out_row) * d)[c] = dv;
+    const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float o0, o1, d0, d1;
+      if (BF16) {
+        o0 = __uint_as_float(ow[e] << 16); o1 = __uint_as_float(ow[e] & 0xffff0000u);
+        d0 = __uint_as_float(dw[e] << 16); d1 = __uint_as_float(dw[e] & 0xffff0000u);
+      } else {
+        const __half2 oh = *reinterpret_cast<const __half2*>(&ow[e]);
+        const __half2 dh = *reinterpret_cast<const __half2*>(&dw[e]);
+        o0 = __low2float(oh); o1 = __high2float(oh);
+        d0 = __low2float(dh); d1 = __high2float(dh);
+      }
+      part += o0 * d0 + o1 * d1;
+    }
+  }
+  for (int off = vec_per_row / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+  if (active && c == 0) {
+    const long long srow = ((long long)b * heads + hh) * n_pad + i;
+    const float l = lse[((long long)b * heads + hh) * n + i];
+    stat_slot[srow] = l * kLog2e;  // +inf stays +inf
+    stat_slot[(long long)batch * heads * n_pad + srow] = part;
+  }
+}
+
+}  // namespace
+
+template <int D>
+void launch_attn_bwd_dq(const CUtensorMap& map_qd, const CUtensorMap& map_kv, const AttnBwdParams& p, int num_sms,
+                        cudaStream_t stream) {
+  auto kern = p.is_bf16 ? attn_bwd_dq_kernel<D, true> : attn_bwd_dq_kernel<D, false>;
+  const size_t smem = sizeof(DqSmem<D>) + 1024;
+  cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "bwd_dq smem attr");
+  const int items = p.batch * p.heads * ((p.n_q + 127) / 128);
+  const int grid = items < num_sms ? items : num_sms;
+  void* args[] = {(void*)&map_qd, (void*)&map_kv, (void*)&p};
+  cuda_check(cudaLaunchKernel((void*)kern, dim3(grid), dim3(NTHREADS), args, smem, stream), "bwd_dq launch");
+}
+
+template <int D>
+void launch_attn_bwd_dkdv(const CUtensorMap& map_qd64, const CUtensorMap& map_kv, const AttnBwdParams& p,
+                          int num_sms, cudaStream_t stream) {
+  auto kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true> : attn_bwd_dkdv_kernel<D, false>;
+  const size_t smem = sizeof(DkvSmem<D>) + 1024;
+  cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+             "bwd_dkdv smem attr");
+  const int items = p.batch * p.kv_heads * ((p.n_k + 127) / 128);
+  const int grid = items < num_sms ? items : num_sms;
+  void* args[] = {(void*)&map_qd64, (void*)&map_kv, (void*)&p};
+  cuda_check(cudaLaunchKernel((void*)kern, dim3(grid), dim3(NTHREADS), args, smem, stream), "bwd_dkdv launch");
+}
+
+void launch_bwd_prep(const void* q, const void* o, const void* dout, const float* lse, void* qdo_slot,
+                     float* stat_slot, int batch, int n, int heads, int d, int n_pad, int is_bf16,
+                     cudaStream_t stream) {
+  const long long threads_total = (long long)batch * n * heads * (d / 8);
+  if (threads_total == 0) return;
+  const int threads = 256;
+  const long long blocks = (threads_total + threads - 1) / threads;
+  auto kern = is_bf16 ? bwd_prep_kernel<true> : bwd_prep_kernel<false>;
+  kern<<<(unsigned)blocks, threads, 0, stream>>>(
+      reinterpret_cast<const uint16_t*>(q), reinterpret_cast<const uint16_t*>(o),
+      reinterpret_cast<const uint16_t*>(dout), lse, reinterpret_cast<uint16_t*>(qdo_slot), stat_slot, batch, n, heads,
+      d, n_pad);
+  cuda_check(cudaGetLastError(), "bwd_prep launch");
+}
+
+template void launch_attn_bwd_dq<64>(const CUtensorMap&, const CUtensorMap&, const AttnBwdParams&, int, cudaStream_t);
+template void launch_attn_bwd_dq<128>(const CUtensorMap&, const CUtensorMap&, const AttnBwdParams&, int, cudaStream_t);
+template void launch_attn_bwd_dkdv<64>(const CUtensorMap&, const CUtensorMap&, const AttnBwdParams&, int, cudaStream_t);
+template void launch_attn_bwd_dkdv<128>(const CUtensorMap&, const CUtensorMap&, const AttnBwdParams&, int, cudaStream_t);
+
+}  // namespace rab

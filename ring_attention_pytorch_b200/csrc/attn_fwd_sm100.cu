@@ -280,7 +280,7 @@ __device__ __forceinline__ void fetch_role(FwdSmem<D>& sm, const AttnFwdParams& 
   const unsigned long long npieces = (p.slot_bytes + FETCH_PIECE - 1) / FETCH_PIECE;
   for (int s = 1; s < p.hop_count; ++s) {
     const int o = p.hop_owner[s];
-    const uint8_t* src = p.kv_peer[o] + (unsigned long long)o * p.slot_bytes;
+    const uint8_t* src = p.kv_peer[o];  // owner o's own slot (peer-mapped staging)
     uint8_t* dst = p.kv_local + (unsigned long long)o * p.slot_bytes;
     auto piece_bytes = [&](unsigned long long pc) -> uint32_t {
       const unsigned long long rem = p.slot_bytes - pc * FETCH_PIECE;

@@ -130,9 +130,9 @@ std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& kv_buf, at::I
     p.kmask_words = km.size(2);
   }
   p.kv_local = reinterpret_cast<uint8_t*>(kv_buf.data_ptr());
-  for (int i = 0; i < world; ++i)
-    p.kv_peer[i] = peer_ptrs[i] ? reinterpret_cast<const uint8_t*>(peer_ptrs[i]) : p.kv_local;
   p.slot_bytes = 2ull * b * kv_heads * n_k * d * 2;
+  for (int i = 0; i < world; ++i)
+    p.kv_peer[i] = peer_ptrs[i] ? reinterpret_cast<const uint8_t*>(peer_ptrs[i]) : p.kv_local + i * p.slot_bytes;
   p.ready = reinterpret_cast<uint32_t*>(ready.data_ptr<int>());
   rab::cuda_check(cudaMemsetAsync(p.ready, 0, sizeof(uint32_t) * world, stream), "ready memset");
 
@@ -153,6 +153,133 @@ std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& kv_buf, at::I
     rab::launch_attn_fwd<64>(map_q, map_kv, p, sm_count(), stream);
   }
   return {o, lse};
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// fused ring attention backward
+// ---------------------------------------------------------------------------------------------
+void bwd_prep(const Tensor& q, const Tensor& o, const Tensor& dout, const Tensor& lse, Tensor qdo_buf,
+              Tensor stat_buf, int64_t rank) {
+  check_16bit(q, "q");
+  TORCH_CHECK(q.is_contiguous() && o.is_contiguous() && dout.is_contiguous() && lse.is_contiguous());
+  TORCH_CHECK(o.scalar_type() == q.scalar_type() && dout.scalar_type() == q.scalar_type());
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && stat_buf.scalar_type() == at::kFloat);
+  const int b = q.size(0), n = q.size(1), h = q.size(2), d = q.size(3);
+  TORCH_CHECK(qdo_buf.dim() == 5 && qdo_buf.is_contiguous() && qdo_buf.size(1) == 2 && qdo_buf.size(2) == b * h &&
+              qdo_buf.size(3) == n && qdo_buf.size(4) == d && qdo_buf.scalar_type() == q.scalar_type());
+  TORCH_CHECK(stat_buf.dim() == 4 && stat_buf.is_contiguous() && stat_buf.size(1) == 2 && stat_buf.size(2) == b * h);
+  const int n_pad = stat_buf.size(3);
+  TORCH_CHECK(n_pad >= n && n_pad % 64 == 0);
+  c10::cuda::CUDAGuard guard(q.device());
+  rab::launch_bwd_prep(q.data_ptr(), o.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(),
+                       qdo_buf[rank].data_ptr(), stat_buf[rank].data_ptr<float>(), b, n, h, d, n_pad,
+                       q.scalar_type() == at::kBFloat16, at::cuda::getCurrentCUDAStream());
+}
+
+struct BwdSetup {
+  rab::AttnBwdParams p;
+  CUtensorMap map_qd128, map_qd64, map_kv;
+};
+
+BwdSetup make_bwd_setup(const Tensor& qdo_buf, const Tensor& kv_buf, const Tensor& stat_buf,
+                        const c10::optional<Tensor>& ready, int64_t ready_target,
+                        const c10::optional<Tensor>& kmask_bits, int64_t batch, int64_t heads, int64_t kv_heads,
+                        int64_t rank, bool causal, int64_t window, double scale, double softclamp, int64_t pos_stride,
+                        int64_t seg_len, at::IntArrayRef base0, at::IntArrayRef base1, int64_t q_pos_offset,
+                        at::IntArrayRef hop_owner) {
+  check_16bit(qdo_buf, "qdo_buf");
+  check_16bit(kv_buf, "kv_buf");
+  TORCH_CHECK(qdo_buf.is_contiguous() && kv_buf.is_contiguous() && stat_buf.is_contiguous());
+  TORCH_CHECK(qdo_buf.dim() == 5 && kv_buf.dim() == 5 && stat_buf.dim() == 4);
+  const int world = kv_buf.size(0), n_k = kv_buf.size(3), d = kv_buf.size(4);
+  const int n_q = qdo_buf.size(3);
+  TORCH_CHECK(qdo_buf.size(0) == world && qdo_buf.size(2) == batch * heads && qdo_buf.size(4) == d);
+  TORCH_CHECK(kv_buf.size(2) == batch * kv_heads && stat_buf.size(0) == world && stat_buf.size(2) == batch * heads);
+  TORCH_CHECK(d == 64 || d == 128);
+  TORCH_CHECK(hop_owner.size() >= 1 && (int)hop_owner.size() <= world && hop_owner[0] == rank);
+  BwdSetup s;
+  rab::AttnBwdParams& p = s.p;
+  std::memset(&p, 0, sizeof(p));
+  p.batch = (int)batch; p.heads = (int)heads; p.kv_heads = (int)kv_heads;
+  p.n_q = n_q; p.n_k = n_k; p.n_pad = stat_buf.size(3);
+  p.world = world; p.rank = (int)rank;
+  p.causal = causal; p.window = (int)window;
+  p.is_bf16 = kv_buf.scalar_type() == at::kBFloat16;
+  p.scale = (float)scale; p.softclamp = (float)softclamp;
+  fill_posmap(p.pos, pos_stride, seg_len, base0, base1, world);
+  p.q_pos_offset = (int)q_pos_offset;
+  p.hop_count = (int)hop_owner.size();
+  for (int i = 0; i < p.hop_count; ++i) p.hop_owner[i] = (int)hop_owner[i];
+  p.stat = stat_buf.data_ptr<float>();
+  if (kmask_bits.has_value()) {
+    const Tensor& km = *kmask_bits;
+    TORCH_CHECK(km.is_cuda() && km.scalar_type() == at::kInt && km.is_contiguous() && km.dim() == 3);
+    TORCH_CHECK(km.size(0) == world && km.size(1) == batch && km.size(2) % 4 == 0 && km.size(2) * 32 >= n_k);
+    p.kmask_bits = reinterpret_cast<const uint32_t*>(km.data_ptr<int>());
+    p.kmask_words = km.size(2);
+  }
+  if (ready.has_value()) {
+    TORCH_CHECK(ready->is_cuda() && ready->scalar_type() == at::kInt && ready->numel() >= world);
+    p.ready = reinterpret_cast<const uint32_t*>(ready->data_ptr<int>());
+    p.ready_target = (uint32_t)ready_target;
+  }
+  uint64_t qdims[4] = {(uint64_t)d, (uint64_t)n_q, (uint64_t)batch * heads, (uint64_t)2 * world};
+  uint64_t qstr[3] = {(uint64_t)d * 2, (uint64_t)n_q * d * 2, (uint64_t)batch * heads * n_q * d * 2};
+  uint32_t qbox128[4] = {64, 128, 1, 1};
+  uint32_t qbox64[4] = {64, 64, 1, 1};
+  s.map_qd128 = rab::make_tmap_bf16(qdo_buf.data_ptr(), 4, qdims, qstr, qbox128, rab::TmapSwizzle::B128);
+  s.map_qd64 = rab::make_tmap_bf16(qdo_buf.data_ptr(), 4, qdims, qstr, qbox64, rab::TmapSwizzle::B128);
+  uint64_t kdims[4] = {(uint64_t)d, (uint64_t)n_k, (uint64_t)batch * kv_heads, (uint64_t)2 * world};
+  uint64_t kstr[3] = {(uint64_t)d * 2, (uint64_t)n_k * d * 2, (uint64_t)batch * kv_heads * n_k * d * 2};
+  uint32_t kbox[4] = {64, 128, 1, 1};
+  s.map_kv = rab::make_tmap_bf16(kv_buf.data_ptr(), 4, kdims, kstr, kbox, rab::TmapSwizzle::B128);
+  return s;
+}
+
+Tensor attn_bwd_dq(const Tensor& qdo_buf, const Tensor& kv_buf, const Tensor& stat_buf,
+                   const c10::optional<Tensor>& ready, int64_t ready_target, const c10::optional<Tensor>& kmask_bits,
+                   int64_t batch, int64_t heads, int64_t kv_heads, int64_t rank, bool causal, int64_t window,
+                   double scale, double softclamp, int64_t pos_stride, int64_t seg_len, at::IntArrayRef base0,
+                   at::IntArrayRef base1, int64_t q_pos_offset, at::IntArrayRef hop_owner) {
+  c10::cuda::CUDAGuard guard(kv_buf.device());
+  BwdSetup s = make_bwd_setup(qdo_buf, kv_buf, stat_buf, ready, ready_target, kmask_bits, batch, heads, kv_heads, rank,
+                              causal, window, scale, softclamp, pos_stride, seg_len, base0, base1, q_pos_offset,
+                              hop_owner);
+  const int d = kv_buf.size(4);
+  Tensor dq = torch::empty({batch, s.p.n_q, heads, d}, kv_buf.options());
+  s.p.dq = dq.data_ptr();
+  auto stream = at::cuda::getCurrentCUDAStream();
+  if (d == 128) {
+    rab::launch_attn_bwd_dq<128>(s.map_qd128, s.map_kv, s.p, sm_count(), stream);
+  } else {
+    rab::launch_attn_bwd_dq<64>(s.map_qd128, s.map_kv, s.p, sm_count(), stream);
+  }
+  return dq;
+}
+
+std::tuple<Tensor, Tensor> attn_bwd_dkdv(const Tensor& qdo_buf, const Tensor& kv_buf, const Tensor& stat_buf,
+                                         const c10::optional<Tensor>& ready, int64_t ready_target,
+                                         const c10::optional<Tensor>& kmask_bits, int64_t batch, int64_t heads,
+                                         int64_t kv_heads, int64_t rank, bool causal, int64_t window, double scale,
+                                         double softclamp, int64_t pos_stride, int64_t seg_len, at::IntArrayRef base0,
+                                         at::IntArrayRef base1, int64_t q_pos_offset, at::IntArrayRef hop_owner) {
+  c10::cuda::CUDAGuard guard(kv_buf.device());
+  BwdSetup s = make_bwd_setup(qdo_buf, kv_buf, stat_buf, ready, ready_target, kmask_bits, batch, heads, kv_heads, rank,
+                              causal, window, scale, softclamp, pos_stride, seg_len, base0, base1, q_pos_offset,
+                              hop_owner);
+  const int d = kv_buf.size(4);
+  Tensor dk = torch::empty({batch, s.p.n_k, kv_heads, d}, kv_buf.options());
+  Tensor dv = torch::empty({batch, s.p.n_k, kv_heads, d}, kv_buf.options());
+  s.p.dk = dk.data_ptr();
+  s.p.dv = dv.data_ptr();
+  auto stream = at::cuda::getCurrentCUDAStream();
+  if (d == 128) {
+    rab::launch_attn_bwd_dkdv<128>(s.map_qd64, s.map_kv, s.p, sm_count(), stream);
+  } else {
+    rab::launch_attn_bwd_dkdv<64>(s.map_qd64, s.map_kv, s.p, sm_count(), stream);
+  }
+  return {dk, dv};
 }
 
 void pack_kv(const Tensor& k, const Tensor& v, Tensor slot) {
@@ -195,6 +322,14 @@ std::tuple<Tensor, Tensor> symm_alloc(int64_t bytes) {
   return {t, handle};
 }
 
+void peer_copy(Tensor dst, int64_t src_ptr, int64_t nbytes) {
+  TORCH_CHECK(dst.is_cuda() && dst.is_contiguous() && (int64_t)dst.nbytes() >= nbytes);
+  c10::cuda::CUDAGuard guard(dst.device());
+  rab::cuda_check(cudaMemcpyAsync(dst.data_ptr(), reinterpret_cast<const void*>(src_ptr), (size_t)nbytes,
+                                  cudaMemcpyDeviceToDevice, at::cuda::getCurrentCUDAStream()),
+                  "peer_copy");
+}
+
 int64_t symm_open(const Tensor& handle) {
   TORCH_CHECK(!handle.is_cuda() && handle.scalar_type() == torch::kUInt8 && handle.numel() == rab::kIpcHandleBytes);
   return reinterpret_cast<int64_t>(rab::symm_open(handle.contiguous().data_ptr<uint8_t>()));
@@ -211,7 +346,16 @@ TORCH_LIBRARY(rab, m) {
         "bool causal, int window, float scale, float softclamp, int pos_stride, int seg_len, int[] base0, int[] "
         "base1, int q_pos_offset, int[] hop_owner) -> (Tensor, Tensor)");
   m.def("pack_kv(Tensor k, Tensor v, Tensor(a!) slot) -> ()");
+  m.def("bwd_prep(Tensor q, Tensor o, Tensor dout, Tensor lse, Tensor(a!) qdo_buf, Tensor(b!) stat_buf, int rank) -> ()");
+  m.def("attn_bwd_dq(Tensor qdo_buf, Tensor kv_buf, Tensor stat_buf, Tensor? ready, int ready_target, Tensor? "
+        "kmask_bits, int batch, int heads, int kv_heads, int rank, bool causal, int window, float scale, float "
+        "softclamp, int pos_stride, int seg_len, int[] base0, int[] base1, int q_pos_offset, int[] hop_owner) -> Tensor");
+  m.def("attn_bwd_dkdv(Tensor qdo_buf, Tensor kv_buf, Tensor stat_buf, Tensor? ready, int ready_target, Tensor? "
+        "kmask_bits, int batch, int heads, int kv_heads, int rank, bool causal, int window, float scale, float "
+        "softclamp, int pos_stride, int seg_len, int[] base0, int[] base1, int q_pos_offset, int[] hop_owner) -> "
+        "(Tensor, Tensor)");
   m.def("device_barrier(int[] pad_ptrs, int rank, int epoch) -> ()");
+  m.def("peer_copy(Tensor(a!) dst, int src_ptr, int nbytes) -> ()");
   m.def("symm_alloc(int bytes) -> (Tensor, Tensor)");
   m.def("symm_open(Tensor handle) -> int");
   m.def("symm_close(int ptr) -> ()");
@@ -221,10 +365,14 @@ TORCH_LIBRARY_IMPL(rab, CUDA, m) {
   m.impl("umma_probe", &umma_probe);
   m.impl("attn_fwd", &attn_fwd);
   m.impl("pack_kv", &pack_kv);
+  m.impl("bwd_prep", &bwd_prep);
+  m.impl("attn_bwd_dq", &attn_bwd_dq);
+  m.impl("attn_bwd_dkdv", &attn_bwd_dkdv);
 }
 
 TORCH_LIBRARY_IMPL(rab, CompositeExplicitAutograd, m) {
   m.impl("device_barrier", &device_barrier);
+  m.impl("peer_copy", &peer_copy);
   m.impl("symm_alloc", &symm_alloc);
   m.impl("symm_open", &symm_open);
   m.impl("symm_close", &symm_close);

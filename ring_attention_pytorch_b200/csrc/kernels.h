@@ -67,7 +67,7 @@ struct AttnFwdParams {
   int kmask_words;
   // in-kernel K/V gather over NVLink
   uint8_t* kv_local;                  // this rank's [world][2][b*hk][n_k][d] buffer
-  const uint8_t* kv_peer[kMaxWorld];  // same buffer on every ring peer (peer-mapped)
+  const uint8_t* kv_peer[kMaxWorld];  // kv_peer[o]: owner o's own [2][b*hk][n_k][d] slot (peer-mapped)
   unsigned long long slot_bytes;      // bytes of one owner slot (K and V)
   uint32_t* ready;                    // [world] arrival counters, zero before launch
 };
@@ -76,6 +76,48 @@ template <int D>
 void launch_attn_fwd(const CUtensorMap& map_q, const CUtensorMap& map_kv, const AttnFwdParams& p, int num_sms,
                      cudaStream_t stream);
 size_t attn_fwd_smem_bytes(int head_dim);
+
+// ------------------------------------------------------------------------------------------------
+// fused ring flash-attention backward: two kernels, no atomics, no cross-rank reduction.
+//   dq kernel   : Q-stationary  (like forward), streams K/V tiles of every visible owner
+//   dkdv kernel : KV-stationary, streams Q / dO / lse / delta tiles of every rank that can see the keys
+// Both read *gathered* buffers: kv_buf [world][2][b*hk][n_k][d] and qdo_buf [world][2][b*h][n_q][d]
+// (16 bit) plus stat_buf [world][2][b*h][n_pad] (fp32: lse*log2e, delta).  Slot `rank` is written
+// locally, the other slots arrive over NVLink (copy engines on a side stream, or an earlier kernel) and
+// are published through the per-owner ready flags.
+// ------------------------------------------------------------------------------------------------
+struct AttnBwdParams {
+  int batch, heads, kv_heads;
+  int n_q, n_k, n_pad;
+  int world, rank;
+  int causal, window, is_bf16;
+  float scale, softclamp;
+  PosMap pos;
+  int q_pos_offset;
+  int hop_count;
+  int hop_owner[kMaxWorld];
+  const float* stat;           // gathered [world][2][b*h][n_pad]
+  void* dq;                    // [b, n_q, h, d]
+  void* dk;                    // [b, n_k, hk, d]
+  void* dv;                    // [b, n_k, hk, d]
+  const uint32_t* kmask_bits;  // [world][batch][kmask_words]
+  int kmask_words;
+  const uint32_t* ready;       // [world] flags: slot o usable once ready[o] >= ready_target (may be null)
+  uint32_t ready_target;
+};
+
+template <int D>
+void launch_attn_bwd_dq(const CUtensorMap& map_qd, const CUtensorMap& map_kv, const AttnBwdParams& p, int num_sms,
+                        cudaStream_t stream);
+template <int D>
+void launch_attn_bwd_dkdv(const CUtensorMap& map_qd64, const CUtensorMap& map_kv, const AttnBwdParams& p,
+                          int num_sms, cudaStream_t stream);
+
+// q, o, do: [b, n, h, d] contiguous 16 bit; lse: [b, h, n] fp32 (natural log).
+// Writes this rank's slot: qdo_slot [2][b*h][n][d] (q, do) and stat_slot [2][b*h][n_pad] (lse*log2e, delta).
+void launch_bwd_prep(const void* q, const void* o, const void* dout, const float* lse, void* qdo_slot,
+                     float* stat_slot, int batch, int n, int heads, int d, int n_pad, int is_bf16,
+                     cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // misc kernels (elementwise_sm100.cu)

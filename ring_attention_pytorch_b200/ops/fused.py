@@ -13,7 +13,8 @@ from typing import List, Optional, Sequence
 import torch
 
 from ring_attention_pytorch_b200.ops import _ext
-from ring_attention_pytorch_b200.parallel.layout import PositionMap, make_position_map, ring_hop_owners
+from ring_attention_pytorch_b200.parallel.layout import (PositionMap, make_position_map, ring_hop_owners,
+                                                          ring_query_owners)
 
 
 def pack_key_mask_bits(mask: torch.Tensor) -> torch.Tensor:
@@ -90,9 +91,87 @@ def emulate_ring_forward(
     outs, lses = [], []
     for r in range(world):
         ready = torch.zeros(world, dtype=torch.int32, device=dev)
-        peers = [bufs[o].data_ptr() for o in range(world)]
+        peers = [bufs[o][o].data_ptr() for o in range(world)]  # owner o's own slot
         o, lse = fused_attn_fwd(qs[r].contiguous(), bufs[r], peers, ready, kbits, kv_heads=hk, rank=r, pm=pm,
                                 causal=causal, window=window, scale=scale, softclamp=softclamp)
         outs.append(o)
         lses.append(lse)
     return outs, lses
+
+
+def pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+def alloc_qdo_buffer(world: int, batch: int, heads: int, n_q: int, d: int, dtype, device) -> torch.Tensor:
+    return torch.empty(world, 2, batch * heads, n_q, d, dtype=dtype, device=device)
+
+
+def alloc_stat_buffer(world: int, batch: int, heads: int, n_q: int, device) -> torch.Tensor:
+    return torch.zeros(world, 2, batch * heads, pad64(n_q), dtype=torch.float32, device=device)
+
+
+def fused_attn_bwd(
+    qdo_buf: torch.Tensor,
+    kv_buf: torch.Tensor,
+    stat_buf: torch.Tensor,
+    kmask_bits: Optional[torch.Tensor],
+    *,
+    batch: int,
+    heads: int,
+    kv_heads: int,
+    rank: int,
+    pm: PositionMap,
+    causal: bool,
+    window: Optional[int],
+    scale: float,
+    softclamp: float = 0.0,
+    q_pos_offset: int = 0,
+    ready_kv: Optional[torch.Tensor] = None,
+    ready_q: Optional[torch.Tensor] = None,
+    ready_target: int = 0,
+):
+    """Run both backward kernels on already gathered buffers; returns (dq, dk, dv)."""
+    ops = _ext.ops()
+    kv_owners = ring_hop_owners(pm, rank, causal, window)
+    q_owners = ring_query_owners(pm, rank, causal, window)
+    common = (kmask_bits, batch, heads, kv_heads, rank, bool(causal), int(window or 0), float(scale), float(softclamp),
+              pm.stride, pm.seg_len, pm.base0, pm.base1, int(q_pos_offset))
+    dq = ops.attn_bwd_dq(qdo_buf, kv_buf, stat_buf, ready_kv, ready_target, *common, kv_owners)
+    dk, dv = ops.attn_bwd_dkdv(qdo_buf, kv_buf, stat_buf, ready_q, ready_target, *common, q_owners)
+    return dq, dk, dv
+
+
+def emulate_ring_backward(
+    qs, ks, vs, outs, lses, douts, *,
+    layout: str = "plain",
+    causal: bool = False,
+    window: Optional[int] = None,
+    softclamp: float = 0.0,
+    key_masks=None,
+    scale: Optional[float] = None,
+):
+    """Backward of :func:`emulate_ring_forward` for every emulated rank on the current device."""
+    ops = _ext.ops()
+    world = len(qs)
+    b, n, h, d = qs[0].shape
+    hk = ks[0].shape[2]
+    dev, dt = qs[0].device, qs[0].dtype
+    pm = make_position_map(layout, world, n)
+    scale = d ** -0.5 if scale is None else scale
+    kv_all = alloc_kv_buffer(world, b, hk, n, d, dt, dev)
+    qdo_all = alloc_qdo_buffer(world, b, h, n, d, dt, dev)
+    stat_all = alloc_stat_buffer(world, b, h, n, dev)
+    for r in range(world):
+        ops.pack_kv(ks[r], vs[r], kv_all[r])
+        ops.bwd_prep(qs[r].contiguous(), outs[r].contiguous(), douts[r].contiguous(), lses[r].contiguous(), qdo_all,
+                     stat_all, r)
+    kbits = None
+    if key_masks is not None:
+        kbits = pack_key_mask_bits(torch.stack(list(key_masks), 0))
+    res = []
+    for r in range(world):
+        # every emulated rank sees the same fully gathered buffers (what the NVLink gather produces)
+        res.append(fused_attn_bwd(qdo_all, kv_all, stat_all, kbits, batch=b, heads=h, kv_heads=hk, rank=r, pm=pm,
+                                  causal=causal, window=window, scale=scale, softclamp=softclamp))
+    return res

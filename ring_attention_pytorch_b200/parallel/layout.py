@@ -78,6 +78,25 @@ def ring_hop_owners(pm: PositionMap, rank: int, causal: bool, window: int | None
     return owners
 
 
+def ring_query_owners(pm: PositionMap, rank: int, causal: bool, window: int | None) -> List[int]:
+    """Ranks whose queries can see keys held by ``rank`` (itself first, then r+1, r+2, ...).
+
+    Used by the KV-stationary backward kernel, which pulls Q / dO / lse / delta instead of K / V.
+    """
+    owners = []
+    klo, khi = pm.pos_range(rank)
+    for s in range(pm.world):
+        o = (rank + s) % pm.world
+        if s > 0 and causal:
+            qlo, qhi = pm.pos_range(o)
+            if klo > qhi:
+                continue
+            if window is not None and window > 0 and qlo - khi > window:
+                continue
+        owners.append(o)
+    return owners
+
+
 def to_layout(x: torch.Tensor, layout: str, world: int, dim: int = 1) -> torch.Tensor:
     """Permute a full sequence so that chunk ``r`` of the result is what rank ``r`` holds."""
     n_total = x.shape[dim]

@@ -103,6 +103,144 @@ def case_fwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=Fa
     return {"max_abs_err": err, "lse_err": lerr, "nan": nan, "ok": (err < 3e-2) and (lerr < 2e-2) and not nan}
 
 
+def case_bwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=False, window=None, softclamp=0.0,
+             kmask=False, dtype="bf16", seed=0):
+    import torch
+    from ring_attention_pytorch_b200.ops.fused import emulate_ring_backward, emulate_ring_forward
+    from ring_attention_pytorch_b200.ops.oracle import attention_with_positions
+    from ring_attention_pytorch_b200.parallel.layout import make_position_map
+
+    hk = hk or h
+    torch.manual_seed(seed)
+    dt = torch.bfloat16 if dtype == "bf16" else torch.float16
+    qs = [torch.randn(b, n, h, d, device="cuda", dtype=dt) for _ in range(world)]
+    ks = [torch.randn(b, n, hk, d, device="cuda", dtype=dt) for _ in range(world)]
+    vs = [torch.randn(b, n, hk, d, device="cuda", dtype=dt) for _ in range(world)]
+    dos = [torch.randn(b, n, h, d, device="cuda", dtype=dt) for _ in range(world)]
+    kms = None
+    if kmask:
+        kms = [torch.rand(b, n, device="cuda") > 0.3 for _ in range(world)]
+    outs, lses = emulate_ring_forward(qs, ks, vs, layout=layout, causal=causal, window=window, softclamp=softclamp,
+                                      key_masks=kms)
+    grads = emulate_ring_backward(qs, ks, vs, outs, lses, dos, layout=layout, causal=causal, window=window,
+                                  softclamp=softclamp, key_masks=kms)
+    torch.cuda.synchronize()
+    # fp32 oracle through autograd
+    pm = make_position_map(layout, world, n)
+    qf = [q.float().requires_grad_() for q in qs]
+    kf = [k.float().requires_grad_() for k in ks]
+    vf = [v.float().requires_grad_() for v in vs]
+    k_all, v_all = torch.cat(kf, 1), torch.cat(vf, 1)
+    k_pos = torch.cat([pm.positions(r, "cuda") for r in range(world)])
+    km = None if kms is None else torch.cat(kms, 1)
+    loss = 0.0
+    for r in range(world):
+        o = attention_with_positions(qf[r], k_all, v_all, pm.positions(r, "cuda"), k_pos, causal=causal, window=window,
+                                     key_mask=km, softclamp_value=softclamp)
+        loss = loss + (o * dos[r].float()).sum()
+    loss.backward()
+    errs = {"dq": 0.0, "dk": 0.0, "dv": 0.0}
+    scale_ref = {"dq": 0.0, "dk": 0.0, "dv": 0.0}
+    nan = False
+    for r in range(world):
+        for name, got, ref in (("dq", grads[r][0], qf[r].grad), ("dk", grads[r][1], kf[r].grad),
+                               ("dv", grads[r][2], vf[r].grad)):
+            errs[name] = max(errs[name], (got.float() - ref).abs().max().item())
+            scale_ref[name] = max(scale_ref[name], ref.abs().max().item())
+            nan = nan or bool(torch.isnan(got.float()).any().item())
+    rel = {k2: errs[k2] / max(scale_ref[k2], 1e-6) for k2 in errs}
+    ok = all(v < 3e-2 for v in rel.values()) and not nan
+    res = {"abs": errs, "rel": rel, "nan": nan, "ok": ok}
+    if not ok:
+        # localise: per rank / tensor / head / 128-row tile error (nan -> 999)
+        detail = {}
+        for r in range(world):
+            for name, got, ref in (("dq", grads[r][0], qf[r].grad), ("dk", grads[r][1], kf[r].grad),
+                                   ("dv", grads[r][2], vf[r].grad)):
+                e = torch.nan_to_num((got.float() - ref).abs(), nan=999.0)
+                nt = (n + 127) // 128
+                pad = nt * 128 - n
+                e = torch.nn.functional.pad(e, (0, 0, 0, 0, 0, pad))
+                tile = e.view(b, nt, 128, e.shape[2], d).amax(dim=(2, 4))  # [b, tile, head]
+                detail[f"r{r}_{name}"] = [[round(x, 3) for x in row] for row in tile[0].tolist()]
+        res["detail_b0_tile_by_head"] = detail
+    return res
+
+
+def case_perf_bwd(n=16384, h=16, d=128, causal=True, iters=5, b=1, hk=None):
+    import torch
+    from ring_attention_pytorch_b200.ops import _ext
+    from ring_attention_pytorch_b200.ops.fused import (alloc_kv_buffer, alloc_qdo_buffer, alloc_stat_buffer,
+                                                       fused_attn_bwd, fused_attn_fwd)
+    from ring_attention_pytorch_b200.parallel.layout import make_position_map
+
+    ops = _ext.ops()
+    hk = hk or h
+    dt = torch.bfloat16
+    q = torch.randn(b, n, h, d, device="cuda", dtype=dt)
+    k = torch.randn(b, n, hk, d, device="cuda", dtype=dt)
+    v = torch.randn(b, n, hk, d, device="cuda", dtype=dt)
+    do = torch.randn(b, n, h, d, device="cuda", dtype=dt)
+    pm = make_position_map("plain", 1, n)
+    kv = alloc_kv_buffer(1, b, hk, n, d, dt, "cuda")
+    qdo = alloc_qdo_buffer(1, b, h, n, d, dt, "cuda")
+    stat = alloc_stat_buffer(1, b, h, n, "cuda")
+    ops.pack_kv(k, v, kv[0])
+    ready = torch.zeros(1, dtype=torch.int32, device="cuda")
+    o, lse = fused_attn_fwd(q, kv, [0], ready, None, kv_heads=hk, rank=0, pm=pm, causal=causal, window=None,
+                            scale=d ** -0.5)
+
+    def run():
+        ops.bwd_prep(q, o, do, lse, qdo, stat, 0)
+        return fused_attn_bwd(qdo, kv, stat, None, batch=b, heads=h, kv_heads=hk, rank=0, pm=pm, causal=causal,
+                              window=None, scale=d ** -0.5)
+
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[len(times) // 2]
+    flops = 2.5 * 4.0 * b * h * n * n * d * (0.5 if causal else 1.0)
+    res = {"ms": ms, "tflops_5gemm_equiv": flops / ms / 1e9, "tflops_executed_7gemm": flops * 1.4 / ms / 1e9}
+    # per-kernel split
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    common = (None, b, h, hk, 0, causal, 0, d ** -0.5, 0.0, pm.stride, pm.seg_len, pm.base0, pm.base1, 0)
+    e[0].record()
+    ops.bwd_prep(q, o, do, lse, qdo, stat, 0)
+    e[1].record()
+    ops.attn_bwd_dq(qdo, kv, stat, None, 0, *common, [0])
+    e[2].record()
+    ops.attn_bwd_dkdv(qdo, kv, stat, None, 0, *common, [0])
+    e[3].record()
+    torch.cuda.synchronize()
+    res["ms_prep"], res["ms_dq"], res["ms_dkdv"] = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])
+    try:
+        from flash_attn import flash_attn_func
+
+        qq, kk, vv = (t.clone().requires_grad_() for t in (q, k, v))
+        out = flash_attn_func(qq, kk, vv, causal=causal)
+        out.backward(do, retain_graph=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            out.backward(do, retain_graph=True)
+        e1.record()
+        torch.cuda.synchronize()
+        res["flash_attn2_bwd_tflops"] = flops / (e0.elapsed_time(e1) / 3) / 1e9
+    except Exception as ex:  # noqa: BLE001
+        res["flash_attn2_bwd_tflops"] = f"n/a: {type(ex).__name__}"
+    res["ok"] = True
+    return res
+
+
 def case_perf(n=16384, h=16, d=128, causal=True, iters=5, b=1, hk=None):
     import torch
     from ring_attention_pytorch_b200.ops import _ext
@@ -188,7 +326,36 @@ CASES = {
     "ring4_plain_window": lambda: case_fwd(world=4, n=256, h=2, causal=True, window=300),
     "ring3_kmask": lambda: case_fwd(world=3, n=200, h=2, kmask=True),
     "ring8_striped_causal_big": lambda: case_fwd(world=8, n=1024, h=8, hk=2, layout="striped", causal=True),
+    # backward, single rank
+    "bwd_d128_n256": lambda: case_bwd(),
+    "bwd_d128_n128_h1": lambda: case_bwd(n=128, h=1),
+    "bwd_d128_n64_h1": lambda: case_bwd(n=64, h=1),
+    "bwd_d128_causal_n512": lambda: case_bwd(n=512, causal=True),
+    "bwd_d128_n300_tail": lambda: case_bwd(n=300, b=2),
+    "bwd_d128_causal_n1000": lambda: case_bwd(n=1000, causal=True, h=4),
+    "bwd_d64_n512": lambda: case_bwd(n=512, d=64, h=4),
+    "bwd_d64_causal_n777": lambda: case_bwd(n=777, d=64, h=4, causal=True),
+    "bwd_gqa_causal": lambda: case_bwd(n=512, h=8, hk=2, causal=True),
+    "bwd_kmask": lambda: case_bwd(n=384, h=2, kmask=True, b=2),
+    "bwd_softclamp": lambda: case_bwd(n=384, h=2, softclamp=20.0),
+    "bwd_window": lambda: case_bwd(n=1024, h=2, causal=True, window=200),
+    "bwd_fp16": lambda: case_bwd(n=512, h=2, causal=True, dtype="fp16"),
+    "bwd_many_items": lambda: case_bwd(n=2048, h=16, b=2, causal=True),
+    # backward, emulated rings
+    "rbwd2_plain_h1": lambda: case_bwd(world=2, n=128, h=1),
+    "rbwd3_plain": lambda: case_bwd(world=3, n=128, h=1),
+    "rbwd3_plain_causal": lambda: case_bwd(world=3, n=128, h=1, causal=True),
+    "rbwd4_plain_causal": lambda: case_bwd(world=4, n=256, h=2, causal=True),
+    "rbwd2_plain": lambda: case_bwd(world=2, n=256, h=2),
+    "rbwd2_plain_causal": lambda: case_bwd(world=2, n=256, h=2, causal=True),
+    "rbwd4_striped_causal": lambda: case_bwd(world=4, n=384, h=4, hk=2, layout="striped", causal=True),
+    "rbwd4_zigzag_causal": lambda: case_bwd(world=4, n=512, h=2, layout="zigzag", causal=True),
+    "rbwd4_plain_window": lambda: case_bwd(world=4, n=256, h=2, causal=True, window=300),
+    "rbwd3_kmask": lambda: case_bwd(world=3, n=200, h=2, kmask=True),
     # performance
+    "perfbwd_causal_16k": lambda: case_perf_bwd(),
+    "perfbwd_full_8k": lambda: case_perf_bwd(n=8192, causal=False),
+    "perfbwd_causal_64k_h8": lambda: case_perf_bwd(n=65536, h=8, iters=3),
     "perf_causal_16k": lambda: case_perf(),
     "perf_full_8k": lambda: case_perf(n=8192, causal=False),
     "perf_causal_64k_h8": lambda: case_perf(n=65536, h=8, iters=3),
@@ -199,7 +366,10 @@ GROUPS = {
     "probe": [c for c in CASES if c.startswith("probe")],
     "fwd": [c for c in CASES if c.startswith("fwd")],
     "ring": [c for c in CASES if c.startswith("ring")],
-    "perf": [c for c in CASES if c.startswith("perf")],
+    "bwd": [c for c in CASES if c.startswith("bwd")],
+    "rbwd": [c for c in CASES if c.startswith("rbwd")],
+    "perfbwd": [c for c in CASES if c.startswith("perfbwd")],
+    "perf": [c for c in CASES if c.startswith("perf_")],
 }
 
 
