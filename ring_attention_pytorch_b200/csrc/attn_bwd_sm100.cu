@@ -80,43 +80,65 @@ __device__ __forceinline__ void dq_decode(const AttnBwdParams& p, int idx, DqIte
   it.qhi += p.q_pos_offset;
 }
 
-struct KvTile {
-  int owner, kt;
-  bool part;
-};
+using DqScan = WarpTileScan<1, false>;
 
-// Sequence of visible 128-key tiles of one dQ item (owners in hop order, tiles ascending).
-struct DqIter {
-  int s = 0, kt = 0;
-  __device__ __forceinline__ bool next(const AttnBwdParams& p, const DqItem& it, KvTile& t) {
-    const int nkt = (p.n_k + 127) / 128;
-    const MaskCfg mc{p.causal, p.window, p.kmask_bits != nullptr};
-    while (s < p.hop_count) {
-      const int o = p.hop_owner[s];
-      while (kt < nkt) {
-        const int k = kt++;
-        const int a = k * 128, bb = min(a + 128, p.n_k) - 1;
-        int klo, khi;
-        pos_range(p.pos, o, a, bb, klo, khi);
-        bool need, part;
-        classify_tile(mc, it.qlo, it.qhi, klo, khi, (a + 128) > p.n_k, need, part);
-        if (need) {
-          t.owner = o;
-          t.kt = k;
-          t.part = part;
-          return true;
-        }
-      }
-      kt = 0;
-      ++s;
+__device__ __forceinline__ void dq_init_scan(DqScan& sc, const AttnBwdParams& p, const DqItem& it) {
+  sc.pm = &p.pos;
+  sc.hop_owner = p.hop_owner;
+  sc.hop_count = p.hop_count;
+  sc.groups = 1;
+  sc.n_stream = p.n_k;
+  sc.tile = 128;
+  sc.stream_off = 0;
+  sc.stat_off = 0;
+  sc.mc = MaskCfg{p.causal, p.window, p.kmask_bits != nullptr};
+  sc.st[0] = StatRange{it.qlo, it.qhi, true, false};
+}
+
+// lane 0 probes the barrier, the result is broadcast so the whole warp stays convergent
+__device__ __forceinline__ bool warp_test(uint64_t* bar, uint32_t parity, int lane) {
+  uint32_t ok = 0;
+  if (lane == 0) ok = mbar_test_wait(bar, parity) ? 1u : 0u;
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+
+// Hands the tiles of one scanner out to two streams alternately (tile j -> stream j & 1) while pulling from
+// the scanner strictly in order.  A stream may run at most one tile ahead of the other.
+template <class Scan>
+struct StreamFeeder {
+  Scan scan;
+  uint32_t seq = 0;
+  bool done = false;
+  ScanTile pend[2];
+  uint32_t pend_j[2];
+  bool pend_valid[2] = {false, false};
+  // returns 1: got a tile, 0: must wait for the other stream, -1: sequence exhausted for this stream
+  __device__ __forceinline__ int fetch(int w, int lane, ScanTile& out, uint32_t& j_out) {
+    if (pend_valid[w]) {
+      out = pend[w];
+      j_out = pend_j[w];
+      pend_valid[w] = false;
+      return 1;
     }
-    return false;
-  }
-  // advance to the n-th next tile (n >= 1); returns false when the sequence ends first
-  __device__ __forceinline__ bool advance(const AttnBwdParams& p, const DqItem& it, KvTile& t, int n) {
-    bool ok = true;
-    for (int i = 0; i < n && ok; ++i) ok = next(p, it, t);
-    return ok;
+    while (!done) {
+      const int par = seq & 1;
+      if (par != w && pend_valid[par]) return 0;
+      ScanTile t;
+      if (!scan.next(lane, t)) {
+        done = true;
+        break;
+      }
+      const uint32_t j = seq++;
+      if (par == w) {
+        out = t;
+        j_out = j;
+        return 1;
+      }
+      pend[par] = t;
+      pend_j[par] = j;
+      pend_valid[par] = true;
+    }
+    return -1;
   }
 };
 
@@ -125,39 +147,46 @@ __device__ __forceinline__ void dq_producer(DqSmem<D>& sm, const AttnBwdParams& 
                                             const CUtensorMap* map_kv) {
   constexpr int NSUB = DqSmem<D>::NSUB;
   constexpr uint32_t TILE = DqSmem<D>::TILE;
+  const int lane = lane_id();
   uint32_t n_item = 0, n_tile = 0;
   uint32_t ready_mask = 1u << p.rank;
   const int total = dq_num_items(p);
   for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
     DqItem it;
     dq_decode(p, idx, it);
-    mbar_wait(&sm.qdo_empty, (n_item & 1) ^ 1, 500);
-    mbar_expect_tx(&sm.qdo_full, 2 * TILE);
+    if (lane == 0) {
+      mbar_wait(&sm.qdo_empty, (n_item & 1) ^ 1, 500);
+      mbar_expect_tx(&sm.qdo_full, 2 * TILE);
 #pragma unroll
-    for (int s = 0; s < NSUB; ++s) {
-      tma_load_4d(sm.q + s * SUB128, map_qd, &sm.qdo_full, s * 64, it.row0, it.b * p.heads + it.h, p.rank * 2);
-      tma_load_4d(sm.dout + s * SUB128, map_qd, &sm.qdo_full, s * 64, it.row0, it.b * p.heads + it.h,
-                  p.rank * 2 + 1);
+      for (int s = 0; s < NSUB; ++s) {
+        tma_load_4d(sm.q + s * SUB128, map_qd, &sm.qdo_full, s * 64, it.row0, it.b * p.heads + it.h, p.rank * 2);
+        tma_load_4d(sm.dout + s * SUB128, map_qd, &sm.qdo_full, s * 64, it.row0, it.b * p.heads + it.h,
+                    p.rank * 2 + 1);
+      }
     }
-    DqIter iter;
-    KvTile t;
-    while (iter.next(p, it, t)) {
-      wait_owner_ready(p, t.owner, ready_mask, 501);
-      const uint32_t ks = n_tile % 3, kph = (n_tile / 3) & 1;
-      mbar_wait(&sm.k_empty[ks], kph ^ 1, 510 + ks);
-      mbar_expect_tx(&sm.k_full[ks], TILE);
+    DqScan scan;
+    dq_init_scan(scan, p, it);
+    ScanTile t;
+    while (scan.next(lane, t)) {
+      if (lane == 0) {
+        wait_owner_ready(p, t.owner, ready_mask, 501);
+        const uint32_t ks = n_tile % 3, kph = (n_tile / 3) & 1;
+        mbar_wait(&sm.k_empty[ks], kph ^ 1, 510 + ks);
+        mbar_expect_tx(&sm.k_full[ks], TILE);
 #pragma unroll
-      for (int s = 0; s < NSUB; ++s)
-        tma_load_4d(sm.k[ks] + s * SUB128, map_kv, &sm.k_full[ks], s * 64, t.kt * 128, it.b * p.kv_heads + it.kvh,
-                    t.owner * 2);
-      const uint32_t vs = n_tile % 2, vph = (n_tile / 2) & 1;
-      mbar_wait(&sm.v_empty[vs], vph ^ 1, 520 + vs);
-      mbar_expect_tx(&sm.v_full[vs], TILE);
+        for (int s = 0; s < NSUB; ++s)
+          tma_load_4d(sm.k[ks] + s * SUB128, map_kv, &sm.k_full[ks], s * 64, t.idx * 128,
+                      it.b * p.kv_heads + it.kvh, t.owner * 2);
+        const uint32_t vs = n_tile % 2, vph = (n_tile / 2) & 1;
+        mbar_wait(&sm.v_empty[vs], vph ^ 1, 520 + vs);
+        mbar_expect_tx(&sm.v_full[vs], TILE);
 #pragma unroll
-      for (int s = 0; s < NSUB; ++s)
-        tma_load_4d(sm.v[vs] + s * SUB128, map_kv, &sm.v_full[vs], s * 64, t.kt * 128, it.b * p.kv_heads + it.kvh,
-                    t.owner * 2 + 1);
+        for (int s = 0; s < NSUB; ++s)
+          tma_load_4d(sm.v[vs] + s * SUB128, map_kv, &sm.v_full[vs], s * 64, t.idx * 128,
+                      it.b * p.kv_heads + it.kvh, t.owner * 2 + 1);
+      }
       n_tile++;
+      __syncwarp();
     }
   }
 }
@@ -170,6 +199,7 @@ __device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, ui
   constexpr uint64_t mnmaj = umma_smem_desc_hi_lo(SUB128, 1024, UMMA_LAYOUT_SW128);
   const uint32_t x_tm[2] = {tmem + 0, tmem + 128};
   const uint32_t dq_tm = tmem + 256;
+  const int lane = lane_id();
 
   uint32_t n_item = 0, tile_base = 0;
   uint32_t cnt[2] = {0, 0};  // tiles completed per stream (global) -> barrier parities
@@ -177,18 +207,17 @@ __device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, ui
   for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
     DqItem it;
     dq_decode(p, idx, it);
-    mbar_wait(&sm.qdo_full, n_item & 1, 600);
-    tc_fence_after();
-
-    DqIter iters[2];
-    KvTile tl[2];
-    int state[2];  // 0: need S, 1: need dP, 2: need dQ, 3: done
-    uint32_t jj[2];
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      jj[w] = w;
-      state[w] = iters[w].advance(p, it, tl[w], w + 1) ? 0 : 3;
+    if (lane == 0) {
+      mbar_wait(&sm.qdo_full, n_item & 1, 600);
+      tc_fence_after();
     }
+    __syncwarp();
+
+    StreamFeeder<DqScan> feed;
+    dq_init_scan(feed.scan, p, it);
+    ScanTile tl[2];
+    int state[2] = {-1, -1};  // -1: need a tile, 0: need S, 1: need dP, 2: need dQ, 3: done
+    uint32_t jj[2] = {0, 0};
     bool dq_started = false;
     uint32_t ntiles = 0;
     const uint32_t qa = smem_u32(sm.q), da = smem_u32(sm.dout);
@@ -196,55 +225,69 @@ __device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, ui
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
         if (state[w] == 3) continue;
+        if (state[w] == -1) {
+          const int r = feed.fetch(w, lane, tl[w], jj[w]);
+          if (r == 0) continue;
+          state[w] = r == 1 ? 0 : 3;
+          if (r != 1) continue;
+        }
         const uint32_t g = tile_base + jj[w];
         const uint32_t ks = g % 3, kph = (g / 3) & 1, vs = g % 2, vph = (g / 2) & 1;
         if (state[w] == 0) {
-          if (!mbar_test_wait(&sm.k_full[ks], kph)) continue;
-          tc_fence_after();
-          const uint32_t ka = smem_u32(sm.k[ks]);
+          if (!warp_test(&sm.k_full[ks], kph, lane)) continue;
+          if (lane == 0) {
+            tc_fence_after();
+            const uint32_t ka = smem_u32(sm.k[ks]);
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
-            umma_ss(x_tm[w], umma_desc(kmaj, qa + off), umma_desc(kmaj, ka + off), idesc_s, kk > 0);
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
+              umma_ss(x_tm[w], umma_desc(kmaj, qa + off), umma_desc(kmaj, ka + off), idesc_s, kk > 0);
+            }
+            umma_commit(&sm.s_full[w]);
           }
-          umma_commit(&sm.s_full[w]);
           state[w] = 1;
         } else if (state[w] == 1) {
-          if (!mbar_test_wait(&sm.v_full[vs], vph)) continue;
-          if (!mbar_test_wait(&sm.s_taken[w], cnt[w] & 1)) continue;
-          tc_fence_after();
-          const uint32_t va = smem_u32(sm.v[vs]);
+          if (!warp_test(&sm.v_full[vs], vph, lane)) continue;
+          if (!warp_test(&sm.s_taken[w], cnt[w] & 1, lane)) continue;
+          if (lane == 0) {
+            tc_fence_after();
+            const uint32_t va = smem_u32(sm.v[vs]);
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
-            umma_ss(x_tm[w], umma_desc(kmaj, da + off), umma_desc(kmaj, va + off), idesc_s, kk > 0);
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
+              umma_ss(x_tm[w], umma_desc(kmaj, da + off), umma_desc(kmaj, va + off), idesc_s, kk > 0);
+            }
+            umma_commit(&sm.dp_full[w]);
+            umma_commit(&sm.v_empty[vs]);
           }
-          umma_commit(&sm.dp_full[w]);
-          umma_commit(&sm.v_empty[vs]);
           state[w] = 2;
         } else {
-          if (!mbar_test_wait(&sm.ds_ready[w], cnt[w] & 1)) continue;
-          if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 610);
-          tc_fence_after();
-          const uint32_t ka = smem_u32(sm.k[ks]);
+          if (!warp_test(&sm.ds_ready[w], cnt[w] & 1, lane)) continue;
+          if (lane == 0) {
+            if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 610);
+            tc_fence_after();
+            const uint32_t ka = smem_u32(sm.k[ks]);
 #pragma unroll
-          for (int kk = 0; kk < 128 / 16; ++kk) {
-            umma_ts(dq_tm, x_tm[w] + kk * 8, umma_desc(mnmaj, ka + kk * 2048), idesc_dq,
-                    (dq_started || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 128 / 16; ++kk) {
+              umma_ts(dq_tm, x_tm[w] + kk * 8, umma_desc(mnmaj, ka + kk * 2048), idesc_dq,
+                      (dq_started || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&sm.k_empty[ks]);
           }
           dq_started = true;
-          umma_commit(&sm.k_empty[ks]);
           cnt[w]++;
           ntiles++;
-          jj[w] += 2;
-          state[w] = iters[w].advance(p, it, tl[w], 2) ? 0 : 3;
+          state[w] = -1;
         }
       }
     }
-    if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 611);
-    umma_commit(&sm.dq_done);
-    umma_commit(&sm.qdo_empty);
+    if (lane == 0) {
+      if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 611);
+      umma_commit(&sm.dq_done);
+      umma_commit(&sm.qdo_empty);
+    }
     tile_base += ntiles;
+    __syncwarp();
   }
 }
 
@@ -254,6 +297,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
   const uint32_t x_tm = tmem + W * 128 + lane_off;
   const uint32_t dq_tm = tmem + 256 + lane_off;
+  const int lane = lane_id();
   uint32_t cnt = 0, n_item = 0;
 
   const bool clamp = p.softclamp > 0.f;
@@ -275,10 +319,12 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
       delta = p.stat[stat_row + (size_t)p.batch * p.heads * p.n_pad + grow];
     }
 
-    DqIter iter;
-    KvTile t;
-    bool ok = iter.advance(p, it, t, W + 1);
-    while (ok) {
+    DqScan scan;
+    dq_init_scan(scan, p, it);
+    ScanTile t;
+    uint32_t jj = 0;
+    while (scan.next(lane, t)) {
+      if (((jj++) & 1u) != (uint32_t)W) continue;
       mbar_wait(&sm.s_full[W], cnt & 1, 700 + W);
       tc_fence_after();
       uint32_t sr[128];
@@ -290,14 +336,14 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
       tc_fence_before();
       mbar_arrive(&sm.s_taken[W]);
 
-      if (t.part) {
-        const int c0 = t.kt * 128;
+      if (t.part[0]) {
+        const int c0 = t.idx * 128;
         const int split = p.pos.seg_len - c0;
         const int a0 = p.pos.base0[t.owner] + p.pos.stride * c0;
         const int a1 = p.pos.base1[t.owner] + p.pos.stride * (c0 - p.pos.seg_len);
         uint32_t mb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
         if (p.kmask_bits != nullptr) {
-          const uint32_t* w = p.kmask_bits + ((size_t)t.owner * p.batch + it.b) * p.kmask_words + (size_t)t.kt * 4;
+          const uint32_t* w = p.kmask_bits + ((size_t)t.owner * p.batch + it.b) * p.kmask_words + (size_t)t.idx * 4;
           mb[0] = w[0]; mb[1] = w[1]; mb[2] = w[2]; mb[3] = w[3];
         }
         const int ncols = p.n_k - c0;
@@ -315,38 +361,57 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
 
       mbar_wait(&sm.dp_full[W], cnt & 1, 710 + W);
       tc_fence_after();
+      // dS = P o (dP - delta) [* (1 - tanh^2) with softclamp]; the softmax scale is folded into the epilogue.
+      // Masked logits are -inf, so exp2 already yields P = 0 on the plain path.
+      if (!clamp) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t dp[32];
-        tmem_ld32(x_tm + c * 32, dp);
-        tc_wait_ld();
-        uint32_t w16[16];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t dp[32];
+          tmem_ld32(x_tm + c * 32, dp);
+          tc_wait_ld();
+          uint32_t w16[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float ds2[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float s = __uint_as_float(sr[c * 32 + 2 * i + e]);
-            float pj, chain = p.scale;
-            if (clamp) {
-              const float th = fast_tanh(s * pre);
-              pj = fast_exp2(fmaf(th, post, -lse2));
-              chain *= (1.f - th * th);
-            } else {
-              pj = fast_exp2(fmaf(s, mul, -lse2));
-            }
-            if (s == -INFINITY) pj = 0.f;
-            ds2[e] = pj * (__uint_as_float(dp[2 * i + e]) - delta) * chain;
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c * 32 + 2 * i]), mul, -lse2));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c * 32 + 2 * i + 1]), mul, -lse2));
+            const float d0 = p0 * (__uint_as_float(dp[2 * i]) - delta);
+            const float d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - delta);
+            w16[i] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
           }
-          w16[i] = BF16 ? pack_bf16x2(ds2[0], ds2[1]) : pack_f16x2(ds2[0], ds2[1]);
+          tmem_st16(x_tm + c * 16, w16);
         }
-        tmem_st16(x_tm + c * 16, w16);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t dp[32];
+          tmem_ld32(x_tm + c * 32, dp);
+          tc_wait_ld();
+          uint32_t w16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float ds2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              // dynamic chunk index: select the logit with a compile-time-indexed switch over the 4 chunks
+              const int jj2 = 2 * i + e;
+              float sv = __uint_as_float(sr[jj2]);
+              if (c == 1) sv = __uint_as_float(sr[32 + jj2]);
+              if (c == 2) sv = __uint_as_float(sr[64 + jj2]);
+              if (c == 3) sv = __uint_as_float(sr[96 + jj2]);
+              const float th = fast_tanh(sv * pre);
+              float pj = fast_exp2(fmaf(th, post, -lse2));
+              if (sv == -INFINITY) pj = 0.f;
+              ds2[e] = pj * (__uint_as_float(dp[jj2]) - delta) * (1.f - th * th);
+            }
+            w16[i] = BF16 ? pack_bf16x2(ds2[0], ds2[1]) : pack_f16x2(ds2[0], ds2[1]);
+          }
+          tmem_st16(x_tm + c * 16, w16);
+        }
       }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&sm.ds_ready[W]);
       cnt++;
-      ok = iter.advance(p, it, t, 2);
     }
 
     // epilogue: warpgroup W converts columns [W*D/2, (W+1)*D/2) of dQ
@@ -354,9 +419,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
     tc_fence_after();
     {
       // the item may have had no visible tile at all: dQ is then zero and TMEM holds stale data
-      DqIter probe;
-      KvTile tt;
-      const bool any = probe.next(p, it, tt);
+      const bool any = jj > 0;
       uint16_t* drow = reinterpret_cast<uint16_t*>(p.dq) +
                        (((size_t)it.b * p.n_q + (row_ok ? grow : 0)) * p.heads + it.h) * D + W * (D / 2);
 #pragma unroll
@@ -372,7 +435,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float a = __uint_as_float(acc[2 * i]), bq = __uint_as_float(acc[2 * i + 1]);
+          const float a = __uint_as_float(acc[2 * i]) * p.scale, bq = __uint_as_float(acc[2 * i + 1]) * p.scale;
           w[i] = BF16 ? pack_bf16x2(a, bq) : pack_f16x2(a, bq);
         }
         if (row_ok) {
@@ -423,10 +486,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_cons
   const uint32_t tmem = sm.tmem_base;
   if (warp < 4) {
     setmaxnreg_dec<72>();
-    if (lane_id() == 0) {
-      if (warp == 0) dq_producer<D>(sm, p, &map_qd, &map_kv);
-      if (warp == 1) dq_mma<D, BF16>(sm, p, tmem);
-    }
+    if (warp == 0) dq_producer<D>(sm, p, &map_qd, &map_kv);
+    if (warp == 1) dq_mma<D, BF16>(sm, p, tmem);
   } else {
     setmaxnreg_inc<216>();
     if (warp < 8) {
@@ -484,58 +545,28 @@ __device__ __forceinline__ void dkv_decode(const AttnBwdParams& p, int idx, DkvI
   it.k_tail = (it.key0 + 128) > p.n_k;
 }
 
-struct QTile {
-  int g, owner, qt;  // query head = g * kv_heads + kvh, rows [qt*64, qt*64+64) of `owner`
-  bool part;
-};
+using DkvScan = WarpTileScan<1, true>;
 
-// Sequence of visible 64-query tiles of one dK/dV item: group heads x owners (hop order) x tiles.
-struct DkvIter {
-  int g = 0, s = 0, qt = 0;
-  __device__ __forceinline__ bool next(const AttnBwdParams& p, const DkvItem& it, QTile& t) {
-    const int nqt = (p.n_q + 63) / 64;
-    const int groups = p.heads / p.kv_heads;
-    const MaskCfg mc{p.causal, p.window, p.kmask_bits != nullptr};
-    while (g < groups) {
-      while (s < p.hop_count) {
-        const int o = p.hop_owner[s];
-        while (qt < nqt) {
-          const int i = qt++;
-          const int a = i * 64, bb = min(a + 64, p.n_q) - 1;
-          int qlo, qhi;
-          pos_range(p.pos, o, a, bb, qlo, qhi);
-          qlo += p.q_pos_offset;
-          qhi += p.q_pos_offset;
-          bool need, part;
-          classify_tile(mc, qlo, qhi, it.klo, it.khi, it.k_tail || (a + 64) > p.n_q, need, part);
-          if (need) {
-            t.g = g;
-            t.owner = o;
-            t.qt = i;
-            t.part = part;
-            return true;
-          }
-        }
-        qt = 0;
-        ++s;
-      }
-      s = 0;
-      ++g;
-    }
-    return false;
-  }
-  __device__ __forceinline__ bool advance(const AttnBwdParams& p, const DkvItem& it, QTile& t, int n) {
-    bool ok = true;
-    for (int i = 0; i < n && ok; ++i) ok = next(p, it, t);
-    return ok;
-  }
-};
+// streamed side = query tiles of 64 rows; rep = index of the query head inside the GQA group
+__device__ __forceinline__ void dkv_init_scan(DkvScan& sc, const AttnBwdParams& p, const DkvItem& it) {
+  sc.pm = &p.pos;
+  sc.hop_owner = p.hop_owner;
+  sc.hop_count = p.hop_count;
+  sc.groups = p.heads / p.kv_heads;
+  sc.n_stream = p.n_q;
+  sc.tile = 64;
+  sc.stream_off = p.q_pos_offset;
+  sc.stat_off = 0;
+  sc.mc = MaskCfg{p.causal, p.window, p.kmask_bits != nullptr};
+  sc.st[0] = StatRange{it.klo, it.khi, true, it.k_tail};
+}
 
 template <int D>
 __device__ __forceinline__ void dkv_producer(DkvSmem<D>& sm, const AttnBwdParams& p, const CUtensorMap* map_qd64,
                                              const CUtensorMap* map_kv) {
   constexpr int NSUB = DkvSmem<D>::NSUB;
   constexpr uint32_t KV_TILE = DkvSmem<D>::KV_TILE, Q_TILE = DkvSmem<D>::Q_TILE;
+  const int lane = lane_id();
   uint32_t n_item = 0, n_tile = 0;
   uint32_t ready_mask = 1u << p.rank;
   const int total = dkv_num_items(p);
@@ -543,32 +574,39 @@ __device__ __forceinline__ void dkv_producer(DkvSmem<D>& sm, const AttnBwdParams
   for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
     DkvItem it;
     dkv_decode(p, idx, it);
-    mbar_wait(&sm.kv_empty, (n_item & 1) ^ 1, 800);
-    mbar_expect_tx(&sm.kv_full, 2 * KV_TILE);
-#pragma unroll
-    for (int s = 0; s < NSUB; ++s) {
-      tma_load_4d(sm.k + s * SUB128, map_kv, &sm.kv_full, s * 64, it.key0, it.b * p.kv_heads + it.kvh, p.rank * 2);
-      tma_load_4d(sm.v + s * SUB128, map_kv, &sm.kv_full, s * 64, it.key0, it.b * p.kv_heads + it.kvh,
-                  p.rank * 2 + 1);
-    }
-    DkvIter iter;
-    QTile t;
-    while (iter.next(p, it, t)) {
-      wait_owner_ready(p, t.owner, ready_mask, 801);
-      const uint32_t st = n_tile % QSTAGES, ph = (n_tile / QSTAGES) & 1;
-      const int h = t.g * p.kv_heads + it.kvh;
-      const int bh = it.b * p.heads + h;
-      mbar_wait(&sm.qd_empty[st], ph ^ 1, 810 + st);
-      mbar_expect_tx(&sm.qd_full[st], 2 * Q_TILE + 2 * 64 * 4);
+    if (lane == 0) {
+      mbar_wait(&sm.kv_empty, (n_item & 1) ^ 1, 800);
+      mbar_expect_tx(&sm.kv_full, 2 * KV_TILE);
 #pragma unroll
       for (int s = 0; s < NSUB; ++s) {
-        tma_load_4d(sm.q[st] + s * SUB64, map_qd64, &sm.qd_full[st], s * 64, t.qt * 64, bh, t.owner * 2);
-        tma_load_4d(sm.dout[st] + s * SUB64, map_qd64, &sm.qd_full[st], s * 64, t.qt * 64, bh, t.owner * 2 + 1);
+        tma_load_4d(sm.k + s * SUB128, map_kv, &sm.kv_full, s * 64, it.key0, it.b * p.kv_heads + it.kvh,
+                    p.rank * 2);
+        tma_load_4d(sm.v + s * SUB128, map_kv, &sm.kv_full, s * 64, it.key0, it.b * p.kv_heads + it.kvh,
+                    p.rank * 2 + 1);
       }
-      const float* srow = p.stat + ((size_t)(t.owner * 2) * p.batch * p.heads + bh) * p.n_pad + (size_t)t.qt * 64;
-      bulk_load_1d(sm.lse2[st], srow, 64 * 4, &sm.qd_full[st]);
-      bulk_load_1d(sm.delta[st], srow + stat_half, 64 * 4, &sm.qd_full[st]);
+    }
+    DkvScan scan;
+    dkv_init_scan(scan, p, it);
+    ScanTile t;
+    while (scan.next(lane, t)) {
+      if (lane == 0) {
+        wait_owner_ready(p, t.owner, ready_mask, 801);
+        const uint32_t st = n_tile % QSTAGES, ph = (n_tile / QSTAGES) & 1;
+        const int h = t.rep * p.kv_heads + it.kvh;
+        const int bh = it.b * p.heads + h;
+        mbar_wait(&sm.qd_empty[st], ph ^ 1, 810 + st);
+        mbar_expect_tx(&sm.qd_full[st], 2 * Q_TILE + 2 * 64 * 4);
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s) {
+          tma_load_4d(sm.q[st] + s * SUB64, map_qd64, &sm.qd_full[st], s * 64, t.idx * 64, bh, t.owner * 2);
+          tma_load_4d(sm.dout[st] + s * SUB64, map_qd64, &sm.qd_full[st], s * 64, t.idx * 64, bh, t.owner * 2 + 1);
+        }
+        const float* srow = p.stat + ((size_t)(t.owner * 2) * p.batch * p.heads + bh) * p.n_pad + (size_t)t.idx * 64;
+        bulk_load_1d(sm.lse2[st], srow, 64 * 4, &sm.qd_full[st]);
+        bulk_load_1d(sm.delta[st], srow + stat_half, 64 * 4, &sm.qd_full[st]);
+      }
       n_tile++;
+      __syncwarp();
     }
   }
 }
@@ -583,6 +621,7 @@ __device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, 
   const uint32_t st_tm[2] = {tmem + 0, tmem + 128};
   const uint32_t dpt_tm[2] = {tmem + 64, tmem + 192};
   const uint32_t dk_tm = tmem + 256, dv_tm = tmem + 256 + D;
+  const int lane = lane_id();
 
   uint32_t n_item = 0, tile_base = 0;
   uint32_t cnt[2] = {0, 0};
@@ -590,18 +629,17 @@ __device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, 
   for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
     DkvItem it;
     dkv_decode(p, idx, it);
-    mbar_wait(&sm.kv_full, n_item & 1, 900);
-    tc_fence_after();
-
-    DkvIter iters[2];
-    QTile tl[2];
-    int state[2];  // 0: need S^T/dP^T, 1: need dV/dK, 3: done
-    uint32_t jj[2];
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      jj[w] = w;
-      state[w] = iters[w].advance(p, it, tl[w], w + 1) ? 0 : 3;
+    if (lane == 0) {
+      mbar_wait(&sm.kv_full, n_item & 1, 900);
+      tc_fence_after();
     }
+    __syncwarp();
+
+    StreamFeeder<DkvScan> feed;
+    dkv_init_scan(feed.scan, p, it);
+    ScanTile tl[2];
+    int state[2] = {-1, -1};  // -1: need a tile, 0: need S^T/dP^T, 1: need dV/dK, 3: done
+    uint32_t jj[2] = {0, 0};
     bool acc_started = false;
     uint32_t ntiles = 0;
     const uint32_t ka = smem_u32(sm.k), va = smem_u32(sm.v);
@@ -609,53 +647,65 @@ __device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, 
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
         if (state[w] == 3) continue;
+        if (state[w] == -1) {
+          const int r = feed.fetch(w, lane, tl[w], jj[w]);
+          if (r == 0) continue;
+          state[w] = r == 1 ? 0 : 3;
+          if (r != 1) continue;
+        }
         const uint32_t g = tile_base + jj[w];
         const uint32_t st = g % QSTAGES, ph = (g / QSTAGES) & 1;
         const uint32_t qa = smem_u32(sm.q[st]), da = smem_u32(sm.dout[st]);
         if (state[w] == 0) {
-          if (!mbar_test_wait(&sm.qd_full[st], ph)) continue;
-          tc_fence_after();
+          if (!warp_test(&sm.qd_full[st], ph, lane)) continue;
+          if (lane == 0) {
+            tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
-            const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
-            umma_ss(st_tm[w], umma_desc(kmaj, ka + offk), umma_desc(kmaj, qa + offq), idesc_s, kk > 0);
-          }
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+              const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+              umma_ss(st_tm[w], umma_desc(kmaj, ka + offk), umma_desc(kmaj, qa + offq), idesc_s, kk > 0);
+            }
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
-            const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
-            umma_ss(dpt_tm[w], umma_desc(kmaj, va + offk), umma_desc(kmaj, da + offq), idesc_s, kk > 0);
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+              const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+              umma_ss(dpt_tm[w], umma_desc(kmaj, va + offk), umma_desc(kmaj, da + offq), idesc_s, kk > 0);
+            }
+            umma_commit(&sm.sdp_full[w]);
           }
-          umma_commit(&sm.sdp_full[w]);
           state[w] = 1;
         } else {
-          if (!mbar_test_wait(&sm.pds_ready[w], cnt[w] & 1)) continue;
-          if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 910);
-          tc_fence_after();
+          if (!warp_test(&sm.pds_ready[w], cnt[w] & 1, lane)) continue;
+          if (lane == 0) {
+            if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 910);
+            tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 64 / 16; ++kk) {
-            umma_ts(dv_tm, st_tm[w] + kk * 8, umma_desc(mnmaj64, da + kk * 2048), idesc_acc,
-                    (acc_started || kk > 0) ? 1u : 0u);
-          }
+            for (int kk = 0; kk < 64 / 16; ++kk) {
+              umma_ts(dv_tm, st_tm[w] + kk * 8, umma_desc(mnmaj64, da + kk * 2048), idesc_acc,
+                      (acc_started || kk > 0) ? 1u : 0u);
+            }
 #pragma unroll
-          for (int kk = 0; kk < 64 / 16; ++kk) {
-            umma_ts(dk_tm, dpt_tm[w] + kk * 8, umma_desc(mnmaj64, qa + kk * 2048), idesc_acc,
-                    (acc_started || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 64 / 16; ++kk) {
+              umma_ts(dk_tm, dpt_tm[w] + kk * 8, umma_desc(mnmaj64, qa + kk * 2048), idesc_acc,
+                      (acc_started || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&sm.qd_empty[st]);
           }
           acc_started = true;
-          umma_commit(&sm.qd_empty[st]);
           cnt[w]++;
           ntiles++;
-          jj[w] += 2;
-          state[w] = iters[w].advance(p, it, tl[w], 2) ? 0 : 3;
+          state[w] = -1;
         }
       }
     }
-    if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 911);
-    umma_commit(&sm.acc_done);
-    umma_commit(&sm.kv_empty);
+    if (lane == 0) {
+      if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 911);
+      umma_commit(&sm.acc_done);
+      umma_commit(&sm.kv_empty);
+    }
     tile_base += ntiles;
+    __syncwarp();
   }
 }
 
@@ -665,6 +715,7 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
   const uint32_t st_tm = tmem + W * 128 + lane_off;
   const uint32_t dpt_tm = tmem + W * 128 + 64 + lane_off;
+  const int lane = lane_id();
   uint32_t cnt = 0, n_item = 0, tile_base = 0;
 
   const bool clamp = p.softclamp > 0.f;
@@ -684,12 +735,13 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
       key_ok = (wbits >> (key & 31)) & 1u;
     }
 
-    DkvIter iter;
-    QTile t;
-    uint32_t jj = W;
-    uint32_t ntiles_w = 0;
-    bool ok = iter.advance(p, it, t, W + 1);
-    while (ok) {
+    DkvScan scan;
+    dkv_init_scan(scan, p, it);
+    ScanTile t;
+    uint32_t jn = 0;
+    while (scan.next(lane, t)) {
+      const uint32_t jj = jn++;
+      if ((jj & 1u) != (uint32_t)W) continue;
       const uint32_t stg = (tile_base + jj) % QSTAGES;
       mbar_wait(&sm.sdp_full[W], cnt & 1, 1000 + W);
       tc_fence_after();
@@ -700,50 +752,74 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
       tmem_ld32(dpt_tm + 32, dp + 32);
       tc_wait_ld();
 
-      const int c0 = t.qt * 64;
-      const int split = p.pos.seg_len - c0;
-      const int a0 = p.pos.base0[t.owner] + p.pos.stride * c0 + p.q_pos_offset;
-      const int a1 = p.pos.base1[t.owner] + p.pos.stride * (c0 - p.pos.seg_len) + p.q_pos_offset;
-      const int ncols = p.n_q - c0;
+      const int c0 = t.idx * 64;
       const float4* l4 = reinterpret_cast<const float4*>(sm.lse2[stg]);
       const float4* d4 = reinterpret_cast<const float4*>(sm.delta[stg]);
       uint32_t pw[32], dw[32];
+      // P^T = exp2(S^T * c - lse[col]); dS^T = P^T o (dP^T - delta[col]).  The softmax scale is folded into the dK
+      // epilogue.  The fast path has no per-element predicate at all; ragged / diagonal / padded tiles and the
+      // softclamp variant take the general path.
+      if (!t.part[0] && !clamp) {
 #pragma unroll
-      for (int q4 = 0; q4 < 16; ++q4) {
-        const float4 lv = l4[q4];
-        const float4 dv = d4[q4];
-        const float ls[4] = {lv.x, lv.y, lv.z, lv.w};
-        const float dl[4] = {dv.x, dv.y, dv.z, dv.w};
-        float pp[4], dd[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = q4 * 4 + e;
-          const float s = __uint_as_float(sr[j]);
-          float pj, chain = p.scale;
-          if (clamp) {
-            const float th = fast_tanh(s * pre);
-            pj = fast_exp2(fmaf(th, post, -ls[e]));
-            chain *= (1.f - th * th);
-          } else {
-            pj = fast_exp2(fmaf(s, mul, -ls[e]));
-          }
-          bool keep = key_ok;
-          if (t.part) {
-            const int pq = (j < split ? a0 : a1) + p.pos.stride * j;
-            keep = keep && (j < ncols);
-            if (p.causal) {
-              keep = keep && (pos_k <= pq);
-              if (p.window > 0) keep = keep && (pq - pos_k <= p.window);
-            }
-          }
-          if (!keep) pj = 0.f;
-          pp[e] = pj;
-          dd[e] = pj * (__uint_as_float(dp[j]) - dl[e]) * chain;
+        for (int q4 = 0; q4 < 16; ++q4) {
+          const float4 lv = l4[q4];
+          const float4 dv = d4[q4];
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 0]), mul, -lv.x));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 1]), mul, -lv.y));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 2]), mul, -lv.z));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 3]), mul, -lv.w));
+          const float e0 = p0 * (__uint_as_float(dp[q4 * 4 + 0]) - dv.x);
+          const float e1 = p1 * (__uint_as_float(dp[q4 * 4 + 1]) - dv.y);
+          const float e2 = p2 * (__uint_as_float(dp[q4 * 4 + 2]) - dv.z);
+          const float e3 = p3 * (__uint_as_float(dp[q4 * 4 + 3]) - dv.w);
+          pw[q4 * 2] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+          pw[q4 * 2 + 1] = BF16 ? pack_bf16x2(p2, p3) : pack_f16x2(p2, p3);
+          dw[q4 * 2] = BF16 ? pack_bf16x2(e0, e1) : pack_f16x2(e0, e1);
+          dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(e2, e3) : pack_f16x2(e2, e3);
         }
-        pw[q4 * 2] = BF16 ? pack_bf16x2(pp[0], pp[1]) : pack_f16x2(pp[0], pp[1]);
-        pw[q4 * 2 + 1] = BF16 ? pack_bf16x2(pp[2], pp[3]) : pack_f16x2(pp[2], pp[3]);
-        dw[q4 * 2] = BF16 ? pack_bf16x2(dd[0], dd[1]) : pack_f16x2(dd[0], dd[1]);
-        dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(dd[2], dd[3]) : pack_f16x2(dd[2], dd[3]);
+      } else {
+        const int split = p.pos.seg_len - c0;
+        const int a0 = p.pos.base0[t.owner] + p.pos.stride * c0 + p.q_pos_offset;
+        const int a1 = p.pos.base1[t.owner] + p.pos.stride * (c0 - p.pos.seg_len) + p.q_pos_offset;
+        const int ncols = p.n_q - c0;
+        const bool part = t.part[0];
+#pragma unroll
+        for (int q4 = 0; q4 < 16; ++q4) {
+          const float4 lv = l4[q4];
+          const float4 dv = d4[q4];
+          const float ls[4] = {lv.x, lv.y, lv.z, lv.w};
+          const float dl[4] = {dv.x, dv.y, dv.z, dv.w};
+          float pp[4], dd[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = q4 * 4 + e;
+            const float sv = __uint_as_float(sr[j]);
+            float pj, chain = 1.f;
+            if (clamp) {
+              const float th = fast_tanh(sv * pre);
+              pj = fast_exp2(fmaf(th, post, -ls[e]));
+              chain = 1.f - th * th;
+            } else {
+              pj = fast_exp2(fmaf(sv, mul, -ls[e]));
+            }
+            bool keep = true;
+            if (part) {
+              const int pq = (j < split ? a0 : a1) + p.pos.stride * j;
+              keep = key_ok && (j < ncols);
+              if (p.causal) {
+                keep = keep && (pos_k <= pq);
+                if (p.window > 0) keep = keep && (pq - pos_k <= p.window);
+              }
+            }
+            if (!keep) pj = 0.f;
+            pp[e] = pj;
+            dd[e] = pj * (__uint_as_float(dp[j]) - dl[e]) * chain;
+          }
+          pw[q4 * 2] = BF16 ? pack_bf16x2(pp[0], pp[1]) : pack_f16x2(pp[0], pp[1]);
+          pw[q4 * 2 + 1] = BF16 ? pack_bf16x2(pp[2], pp[3]) : pack_f16x2(pp[2], pp[3]);
+          dw[q4 * 2] = BF16 ? pack_bf16x2(dd[0], dd[1]) : pack_f16x2(dd[0], dd[1]);
+          dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(dd[2], dd[3]) : pack_f16x2(dd[2], dd[3]);
+        }
       }
       tmem_st32(st_tm, pw);
       tmem_st32(dpt_tm, dw);
@@ -751,26 +827,14 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
       tc_fence_before();
       mbar_arrive(&sm.pds_ready[W]);
       cnt++;
-      ntiles_w++;
-      jj += 2;
-      ok = iter.advance(p, it, t, 2);
     }
-    // both warpgroups need the item's total tile count to keep the stage ring in step
-    {
-      DkvIter count_iter;
-      QTile tt;
-      uint32_t n = 0;
-      while (count_iter.next(p, it, tt)) ++n;
-      tile_base += n;
-    }
+    tile_base += jn;  // both warpgroups walk the whole sequence, so the stage ring stays in step
 
     // epilogue: warpgroup 0 writes dK, warpgroup 1 writes dV
     mbar_wait(&sm.acc_done, n_item & 1, 1010 + W);
     tc_fence_after();
     {
-      DkvIter probe;
-      QTile tt;
-      const bool any = probe.next(p, it, tt);
+      const bool any = jn > 0;
       const uint32_t acc_tm = tmem + 256 + (W == 0 ? 0 : D) + lane_off;
       const bool row_ok = key < p.n_k;
       uint16_t* out = reinterpret_cast<uint16_t*>(W == 0 ? p.dk : p.dv) +
@@ -788,7 +852,8 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float a = __uint_as_float(acc[2 * i]), bq = __uint_as_float(acc[2 * i + 1]);
+          const float osc = W == 0 ? p.scale : 1.f;  // dK carries the folded softmax scale
+          const float a = __uint_as_float(acc[2 * i]) * osc, bq = __uint_as_float(acc[2 * i + 1]) * osc;
           w[i] = BF16 ? pack_bf16x2(a, bq) : pack_f16x2(a, bq);
         }
         if (row_ok) {
@@ -835,10 +900,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
   const uint32_t tmem = sm.tmem_base;
   if (warp < 4) {
     setmaxnreg_dec<72>();
-    if (lane_id() == 0) {
-      if (warp == 0) dkv_producer<D>(sm, p, &map_qd64, &map_kv);
-      if (warp == 1) dkv_mma<D, BF16>(sm, p, tmem);
-    }
+    if (warp == 0) dkv_producer<D>(sm, p, &map_qd64, &map_kv);
+    if (warp == 1) dkv_mma<D, BF16>(sm, p, tmem);
   } else {
     setmaxnreg_inc<216>();
     if (warp < 8) {

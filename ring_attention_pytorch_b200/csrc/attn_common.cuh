@@ -58,4 +58,110 @@ __device__ __forceinline__ void classify_tile(const MaskCfg& mc, int qlo, int qh
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative tile scanner.
+//
+// Every warp role (TMA producer, MMA issuer, softmax warps) replays the same deterministic sequence of
+// streamed tiles.  Classifying tiles one at a time on a single thread puts ~100 dependent instructions
+// between two tcgen05.mma issues; here the 32 lanes of a warp classify 32 tiles at once and publish the
+// result as ballot masks, so advancing to the next visible tile is a find-first-set.
+//
+// Sequence order: repeat `groups` times { for hop s in [0, hop_count) { tiles ascending } }.
+// All 32 lanes must call next() convergently; the scanner state is warp-uniform.
+// ------------------------------------------------------------------------------------------------
+struct StatRange {
+  int lo, hi;   // position range of the stationary tile
+  bool valid;   // false: the stationary tile does not exist (e.g. second Q tile beyond n_q)
+  bool tail;    // the stationary tile is ragged (forces per-element masking)
+};
+
+struct ScanTile {
+  int rep;       // group repetition index
+  int owner;     // ring rank that owns the streamed tile
+  int idx;       // tile index inside the owner's shard
+  bool need[2];
+  bool part[2];
+};
+
+template <int NSTAT, bool STREAM_IS_Q>
+struct WarpTileScan {
+  const PosMap* pm;
+  const int* hop_owner;
+  int hop_count, groups;
+  int n_stream, tile, stream_off, stat_off;
+  MaskCfg mc;
+  StatRange st[NSTAT];
+  // iteration state (warp-uniform)
+  int rep = 0, s = 0, base = 0;
+  uint32_t need[NSTAT], part[NSTAT], any = 0;
+  bool primed = false;
+
+  __device__ __forceinline__ void load_chunk(int lane) {
+    const int o = hop_owner[s];
+    const int t = base + lane;
+    const int nt = (n_stream + tile - 1) / tile;
+    bool nd[NSTAT], pt[NSTAT];
+#pragma unroll
+    for (int i = 0; i < NSTAT; ++i) nd[i] = pt[i] = false;
+    if (t < nt) {
+      const int a = t * tile, b = min(a + tile, n_stream) - 1;
+      int lo, hi;
+      pos_range(*pm, o, a, b, lo, hi);
+      lo += stream_off;
+      hi += stream_off;
+      const bool tail = (a + tile) > n_stream;
+#pragma unroll
+      for (int i = 0; i < NSTAT; ++i) {
+        if (st[i].valid) {
+          if (STREAM_IS_Q) {
+            classify_tile(mc, lo, hi, st[i].lo + stat_off, st[i].hi + stat_off, tail || st[i].tail, nd[i], pt[i]);
+          } else {
+            classify_tile(mc, st[i].lo + stat_off, st[i].hi + stat_off, lo, hi, tail || st[i].tail, nd[i], pt[i]);
+          }
+        }
+      }
+    }
+    any = 0;
+#pragma unroll
+    for (int i = 0; i < NSTAT; ++i) {
+      need[i] = __ballot_sync(0xffffffffu, nd[i]);
+      part[i] = __ballot_sync(0xffffffffu, pt[i]);
+      any |= need[i];
+    }
+  }
+
+  __device__ __forceinline__ bool next(int lane, ScanTile& t) {
+    const int nt = (n_stream + tile - 1) / tile;
+    while (true) {
+      if (!primed) {
+        if (rep >= groups) return false;
+        load_chunk(lane);
+        primed = true;
+      }
+      if (any) {
+        const int bit = __ffs(any) - 1;
+        any &= any - 1;
+        t.rep = rep;
+        t.owner = hop_owner[s];
+        t.idx = base + bit;
+#pragma unroll
+        for (int i = 0; i < NSTAT; ++i) {
+          t.need[i] = (need[i] >> bit) & 1u;
+          t.part[i] = (part[i] >> bit) & 1u;
+        }
+        return true;
+      }
+      primed = false;
+      base += 32;
+      if (base >= nt) {
+        base = 0;
+        if (++s >= hop_count) {
+          s = 0;
+          ++rep;
+        }
+      }
+    }
+  }
+};
+
 }  // namespace rab

@@ -53,11 +53,6 @@ struct Item {
   int qlo[2], qhi[2];
 };
 
-struct TileInfo {
-  int owner, kt;
-  bool need[2], part[2];
-};
-
 __device__ __forceinline__ int num_items(const AttnFwdParams& p) {
   const int nqp = (p.n_q + 2 * BM - 1) / (2 * BM);
   return p.batch * p.heads * nqp;
@@ -89,49 +84,31 @@ __device__ __forceinline__ void decode_item(const AttnFwdParams& p, int idx, Ite
   }
 }
 
-struct KvIter {
-  int s = 0, kt = 0;
-  __device__ __forceinline__ bool next(const AttnFwdParams& p, const Item& it, TileInfo& ti) {
-    const int nkt = (p.n_k + BN - 1) / BN;
-    const MaskCfg mc{p.causal, p.window, p.kmask_bits != nullptr};
-    while (s < p.hop_count) {
-      const int o = p.hop_owner[s];
-      while (kt < nkt) {
-        const int k = kt++;
-        const int a = k * BN, bb = min(a + BN, p.n_k) - 1;
-        int klo, khi;
-        pos_range(p.pos, o, a, bb, klo, khi);
-        const bool tail = (a + BN) > p.n_k;
-        bool any = false;
+using FwdScan = WarpTileScan<2, false>;
+
+__device__ __forceinline__ void init_scan(FwdScan& sc, const AttnFwdParams& p, const Item& it) {
+  sc.pm = &p.pos;
+  sc.hop_owner = p.hop_owner;
+  sc.hop_count = p.hop_count;
+  sc.groups = 1;
+  sc.n_stream = p.n_k;
+  sc.tile = BN;
+  sc.stream_off = 0;
+  sc.stat_off = 0;
+  sc.mc = MaskCfg{p.causal, p.window, p.kmask_bits != nullptr};
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          bool need = false, part = false;
-          if (it.tvalid[t]) classify_tile(mc, it.qlo[t], it.qhi[t], klo, khi, tail, need, part);
-          ti.need[t] = need;
-          ti.part[t] = part;
-          any |= need;
-        }
-        if (any) {
-          ti.owner = o;
-          ti.kt = k;
-          return true;
-        }
-      }
-      kt = 0;
-      ++s;
-    }
-    return false;
-  }
-};
+  for (int t = 0; t < 2; ++t) sc.st[t] = StatRange{it.qlo[t], it.qhi[t], it.tvalid[t], false};
+}
 
 // ------------------------------------------------------------------------------------------------
-// warp 0: TMA producer
+// warp 0: TMA producer (all 32 lanes scan tiles, lane 0 issues)
 // ------------------------------------------------------------------------------------------------
 template <int D>
 __device__ __forceinline__ void producer_role(FwdSmem<D>& sm, const AttnFwdParams& p, const CUtensorMap* map_q,
-                              const CUtensorMap* map_kv) {
+                                              const CUtensorMap* map_kv) {
   constexpr int NSUB = FwdSmem<D>::NSUB;
   constexpr uint32_t TILE_BYTES = FwdSmem<D>::TILE_BYTES;
+  const int lane = lane_id();
   uint32_t n_slot = 0;
   uint32_t items_t[2] = {0, 0};
   uint32_t ready_mask = 1u << p.rank;
@@ -142,38 +119,47 @@ __device__ __forceinline__ void producer_role(FwdSmem<D>& sm, const AttnFwdParam
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       if (!it.tvalid[t]) continue;
-      mbar_wait(&sm.q_empty[t], (items_t[t] & 1) ^ 1, 100 + t);
-      mbar_expect_tx(&sm.q_full[t], TILE_BYTES);
-#pragma unroll
-      for (int s = 0; s < NSUB; ++s)
-        tma_load_4d(sm.q[t] + s * SUB_BYTES, map_q, &sm.q_full[t], s * 64, it.h, it.row0[t], it.b);
-      items_t[t]++;
-    }
-    KvIter iter;
-    TileInfo ti;
-    while (iter.next(p, it, ti)) {
-      if (!((ready_mask >> ti.owner) & 1u)) {
-        spin_until_ge_gpu(&p.ready[ti.owner], gridDim.x, 110);
-        fence_proxy_async_global();
-        ready_mask |= 1u << ti.owner;
-      }
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        const uint32_t slot = n_slot % NSLOT, ph = (n_slot / NSLOT) & 1;
-        mbar_wait(&sm.kv_empty[slot], ph ^ 1, 120 + slot);
-        mbar_expect_tx(&sm.kv_full[slot], TILE_BYTES);
+      if (lane == 0) {
+        mbar_wait(&sm.q_empty[t], (items_t[t] & 1) ^ 1, 100 + t);
+        mbar_expect_tx(&sm.q_full[t], TILE_BYTES);
 #pragma unroll
         for (int s = 0; s < NSUB; ++s)
-          tma_load_4d(sm.kv[slot] + s * SUB_BYTES, map_kv, &sm.kv_full[slot], s * 64, ti.kt * BN,
-                      it.b * p.kv_heads + it.kvh, ti.owner * 2 + which);
-        n_slot++;
+          tma_load_4d(sm.q[t] + s * SUB_BYTES, map_q, &sm.q_full[t], s * 64, it.h, it.row0[t], it.b);
       }
+      items_t[t]++;
+    }
+    FwdScan scan;
+    init_scan(scan, p, it);
+    ScanTile ti;
+    while (scan.next(lane, ti)) {
+      if (!((ready_mask >> ti.owner) & 1u)) {
+        if (lane == 0) {
+          spin_until_ge_gpu(&p.ready[ti.owner], gridDim.x, 110);
+          fence_proxy_async_global();
+        }
+        ready_mask |= 1u << ti.owner;
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t n = n_slot + which;
+          const uint32_t slot = n % NSLOT, ph = (n / NSLOT) & 1;
+          mbar_wait(&sm.kv_empty[slot], ph ^ 1, 120 + slot);
+          mbar_expect_tx(&sm.kv_full[slot], TILE_BYTES);
+#pragma unroll
+          for (int s = 0; s < NSUB; ++s)
+            tma_load_4d(sm.kv[slot] + s * SUB_BYTES, map_kv, &sm.kv_full[slot], s * 64, ti.idx * BN,
+                        it.b * p.kv_heads + it.kvh, ti.owner * 2 + which);
+        }
+      }
+      n_slot += 2;
+      __syncwarp();
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// warp 1: MMA issuer
+// warp 1: MMA issuer (all 32 lanes scan tiles, lane 0 issues tcgen05.mma)
 // ------------------------------------------------------------------------------------------------
 template <int D, bool BF16>
 __device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p, uint32_t tmem) {
@@ -184,13 +170,14 @@ __device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p,
   // MN-major operand (V as B of P V): 64-wide d sub-tiles SUB_BYTES apart, 8-row kv groups 1024 B apart.
   constexpr uint64_t vmaj_static = umma_smem_desc_hi_lo(SUB_BYTES, 1024, UMMA_LAYOUT_SW128);
 
+  const int lane = lane_id();
   uint32_t n_kv = 0;
   uint32_t cnt_p[2] = {0, 0};
   uint32_t items_t[2] = {0, 0};
   const uint32_t s_tm[2] = {tmem + 0, tmem + 128};
   const uint32_t o_tm[2] = {tmem + 256, tmem + 256 + D};
 
-  auto issue_qk = [&](int t, uint32_t kslot) {
+  auto issue_qk = [&](int t, uint32_t kslot) {  // lane 0 only
     const uint32_t qa = smem_u32(sm.q[t]);
     const uint32_t ka = smem_u32(sm.kv[kslot]);
 #pragma unroll
@@ -205,16 +192,19 @@ __device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p,
   for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
     Item it;
     decode_item(p, idx, it);
+    if (lane == 0) {
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
-      if (it.tvalid[t]) mbar_wait(&sm.q_full[t], items_t[t] & 1, 200 + t);
-    tc_fence_after();
+      for (int t = 0; t < 2; ++t)
+        if (it.tvalid[t]) mbar_wait(&sm.q_full[t], items_t[t] & 1, 200 + t);
+      tc_fence_after();
+    }
 
-    KvIter iter;
-    TileInfo cur, nxt;
-    bool has = iter.next(p, it, cur);
+    FwdScan scan;
+    init_scan(scan, p, it);
+    ScanTile cur, nxt;
+    bool has = scan.next(lane, cur);
     bool pv_started[2] = {false, false};
-    if (has) {
+    if (has && lane == 0) {
       const uint32_t ks = (2 * n_kv) % NSLOT, kph = ((2 * n_kv) / NSLOT) & 1;
       mbar_wait(&sm.kv_full[ks], kph, 210);
       tc_fence_after();
@@ -224,48 +214,58 @@ __device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p,
       umma_commit(&sm.kv_empty[ks]);
     }
     while (has) {
-      const bool hasn = iter.next(p, it, nxt);
-      const uint32_t vs = (2 * n_kv + 1) % NSLOT, vph = ((2 * n_kv + 1) / NSLOT) & 1;
-      const uint32_t ksn = (2 * n_kv + 2) % NSLOT, kphn = ((2 * n_kv + 2) / NSLOT) & 1;
-      mbar_wait(&sm.kv_full[vs], vph, 220);
-      tc_fence_after();
-      bool kwaited = false;
-      const uint32_t va = smem_u32(sm.kv[vs]);
+      const bool hasn = scan.next(lane, nxt);
+      if (lane == 0) {
+        const uint32_t vs = (2 * n_kv + 1) % NSLOT, vph = ((2 * n_kv + 1) / NSLOT) & 1;
+        const uint32_t ksn = (2 * n_kv + 2) % NSLOT, kphn = ((2 * n_kv + 2) / NSLOT) & 1;
+        mbar_wait(&sm.kv_full[vs], vph, 220);
+        tc_fence_after();
+        bool kwaited = false;
+        const uint32_t va = smem_u32(sm.kv[vs]);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (cur.need[t]) {
+            if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 230 + t);
+            mbar_wait(&sm.p_ready[t], cnt_p[t] & 1, 240 + t);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < BN / 16; ++kk) {
+              umma_ts(o_tm[t], s_tm[t] + kk * 8, umma_desc(vmaj_static, va + kk * 2048), idesc_pv,
+                      (pv_started[t] || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&sm.o_done[t]);
+          }
+          if (hasn && nxt.need[t]) {
+            if (!kwaited) {
+              mbar_wait(&sm.kv_full[ksn], kphn, 250);
+              tc_fence_after();
+              kwaited = true;
+            }
+            issue_qk(t, ksn);
+          }
+        }
+        umma_commit(&sm.kv_empty[vs]);
+        if (hasn) umma_commit(&sm.kv_empty[ksn]);
+      }
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (cur.need[t]) {
-          if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 230 + t);
-          mbar_wait(&sm.p_ready[t], cnt_p[t] & 1, 240 + t);
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < BN / 16; ++kk) {
-            umma_ts(o_tm[t], s_tm[t] + kk * 8, umma_desc(vmaj_static, va + kk * 2048), idesc_pv,
-                    (pv_started[t] || kk > 0) ? 1u : 0u);
-          }
           pv_started[t] = true;
-          umma_commit(&sm.o_done[t]);
           cnt_p[t]++;
         }
-        if (hasn && nxt.need[t]) {
-          if (!kwaited) {
-            mbar_wait(&sm.kv_full[ksn], kphn, 250);
-            tc_fence_after();
-            kwaited = true;
-          }
-          issue_qk(t, ksn);
-        }
       }
-      umma_commit(&sm.kv_empty[vs]);
-      if (hasn) umma_commit(&sm.kv_empty[ksn]);
       n_kv++;
       cur = nxt;
       has = hasn;
+      __syncwarp();
     }
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       if (!it.tvalid[t]) continue;
-      if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 260 + t);
-      umma_commit(&sm.q_empty[t]);
+      if (lane == 0) {
+        if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 260 + t);
+        umma_commit(&sm.q_empty[t]);
+      }
       items_t[t]++;
     }
   }
@@ -329,6 +329,7 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
   const uint32_t s_tm = tmem + t * 128 + lane_off;
   const uint32_t o_tm = tmem + 256 + t * D + lane_off;
+  const int lane = lane_id();
   uint32_t cnt = 0;
 
   const bool clamp = p.softclamp > 0.f;
@@ -350,9 +351,10 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
     bool have_o = false;
     uint32_t cnt_item = 0;
 
-    KvIter iter;
-    TileInfo ti;
-    while (iter.next(p, it, ti)) {
+    FwdScan scan;
+    init_scan(scan, p, it);
+    ScanTile ti;
+    while (scan.next(lane, ti)) {
       if (!ti.need[t]) continue;
       mbar_wait(&sm.s_full[t], cnt & 1, 400 + t);
       tc_fence_after();
@@ -368,14 +370,14 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
         for (int j = 0; j < 128; ++j) sr[j] = __float_as_uint(fast_tanh(__uint_as_float(sr[j]) * pre) * post);
       }
       if (ti.part[t]) {
-        const int c0 = ti.kt * BN;
+        const int c0 = ti.idx * BN;
         const int split = p.pos.seg_len - c0;
         const int a0 = p.pos.base0[ti.owner] + p.pos.stride * c0;
         const int a1 = p.pos.base1[ti.owner] + p.pos.stride * (c0 - p.pos.seg_len);
         uint32_t mb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
         if (p.kmask_bits != nullptr) {
           const uint32_t* w =
-              p.kmask_bits + ((size_t)ti.owner * p.batch + it.b) * p.kmask_words + (size_t)ti.kt * 4;
+              p.kmask_bits + ((size_t)ti.owner * p.batch + it.b) * p.kmask_words + (size_t)ti.idx * 4;
           mb[0] = w[0]; mb[1] = w[1]; mb[2] = w[2]; mb[3] = w[3];
         }
         const int ncols = p.n_k - c0;  // columns >= ncols are beyond the end of the slot
@@ -391,9 +393,16 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
         }
       }
 
-      float mx = __uint_as_float(sr[0]);
+      // four independent chains (ILP) instead of one 127-deep dependency chain
+      float mx4[4];
 #pragma unroll
-      for (int j = 1; j < 128; ++j) mx = fmaxf(mx, __uint_as_float(sr[j]));
+      for (int a = 0; a < 4; ++a) mx4[a] = __uint_as_float(sr[a]);
+#pragma unroll
+      for (int j = 4; j < 128; j += 4) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) mx4[a] = fmaxf(mx4[a], __uint_as_float(sr[j + a]));
+      }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       mx *= mul;
 
       // lazy rescale: only when the running max moved by more than 2^8 (warp-uniform decision)
@@ -417,17 +426,19 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
         m_used = m_new;
       }
       const float m_eff = (m_used == -INFINITY) ? 0.f : m_used;
-      float lsum0 = 0.f, lsum1 = 0.f;
+      float lsum[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) lsum[a] = 0.f;
       uint32_t pk2[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
         const float p0 = fast_exp2(fmaf(__uint_as_float(sr[2 * j]), mul, -m_eff));
         const float p1 = fast_exp2(fmaf(__uint_as_float(sr[2 * j + 1]), mul, -m_eff));
-        lsum0 += p0;
-        lsum1 += p1;
+        lsum[(2 * j) & 7] += p0;
+        lsum[(2 * j + 1) & 7] += p1;
         pk2[j] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
       }
-      l += lsum0 + lsum1;
+      l += ((lsum[0] + lsum[1]) + (lsum[2] + lsum[3])) + ((lsum[4] + lsum[5]) + (lsum[6] + lsum[7]));
       tmem_st32(s_tm + 0, pk2);
       tmem_st32(s_tm + 32, pk2 + 32);
       tc_wait_st();
@@ -516,14 +527,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
   if (warp < 4) {
     setmaxnreg_dec<72>();
-    if (lane_id() == 0) {
-      if (warp == 0) {
-        producer_role<D>(sm, p, &map_q, &map_kv);
-      } else if (warp == 1) {
-        mma_role<D, BF16>(sm, p, tmem);
-      } else if (warp == 2) {
-        fetch_role<D>(sm, p);
-      }
+    if (warp == 0) {
+      producer_role<D>(sm, p, &map_q, &map_kv);
+    } else if (warp == 1) {
+      mma_role<D, BF16>(sm, p, tmem);
+    } else if (warp == 2) {
+      if (lane_id() == 0) fetch_role<D>(sm, p);
     }
   } else {
     setmaxnreg_inc<216>();

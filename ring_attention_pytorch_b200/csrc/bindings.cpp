@@ -282,6 +282,66 @@ std::tuple<Tensor, Tensor> attn_bwd_dkdv(const Tensor& qdo_buf, const Tensor& kv
   return {dk, dv};
 }
 
+// ---------------------------------------------------------------------------------------------
+// tree-attention decode
+// ---------------------------------------------------------------------------------------------
+void tree_decode_partial(const Tensor& q, const c10::optional<Tensor>& k, const c10::optional<Tensor>& v,
+                         const c10::optional<Tensor>& k_scale, const c10::optional<Tensor>& v_scale, Tensor scratch,
+                         Tensor partial, int64_t kv_heads, int64_t splits, double scale) {
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kFloat && q.is_contiguous() && q.dim() == 3);
+  const int b = q.size(0), h = q.size(1), d = q.size(2);
+  TORCH_CHECK(d == 64 || d == 128, "tree decode supports head dim 64 or 128");
+  TORCH_CHECK(partial.is_cuda() && partial.scalar_type() == at::kFloat && partial.is_contiguous() &&
+              partial.numel() >= (int64_t)b * h * (d + 2));
+  int n = 0, kind = 0;
+  const void* kp = nullptr;
+  const void* vp = nullptr;
+  if (k.has_value()) {
+    TORCH_CHECK(v.has_value() && k->is_contiguous() && v->is_contiguous() && k->dim() == 4 && k->sizes() == v->sizes());
+    TORCH_CHECK(k->size(0) == b && k->size(1) == kv_heads && k->size(3) == d);
+    n = k->size(2);
+    if (k->scalar_type() == at::kBFloat16) kind = 0;
+    else if (k->scalar_type() == at::kHalf) kind = 1;
+    else if (k->scalar_type() == at::kFloat8_e4m3fn) kind = 2;
+    else TORCH_CHECK(false, "k/v must be bf16, fp16 or float8_e4m3fn");
+    TORCH_CHECK(v->scalar_type() == k->scalar_type());
+    kp = k->data_ptr();
+    vp = v->data_ptr();
+  }
+  const float* ksp = nullptr;
+  const float* vsp = nullptr;
+  if (k_scale.has_value()) {
+    TORCH_CHECK(k_scale->scalar_type() == at::kFloat && k_scale->numel() == b * kv_heads && k_scale->is_contiguous());
+    ksp = k_scale->data_ptr<float>();
+  }
+  if (v_scale.has_value()) {
+    TORCH_CHECK(v_scale->scalar_type() == at::kFloat && v_scale->numel() == b * kv_heads && v_scale->is_contiguous());
+    vsp = v_scale->data_ptr<float>();
+  }
+  TORCH_CHECK(scratch.scalar_type() == at::kFloat && scratch.is_contiguous() &&
+              scratch.numel() >= (int64_t)b * kv_heads * splits * (h / kv_heads) * (d + 2));
+  c10::cuda::CUDAGuard guard(q.device());
+  rab::launch_tree_decode_partial(q.data_ptr<float>(), kp, vp, ksp, vsp, scratch.data_ptr<float>(),
+                                  partial.data_ptr<float>(), b, h, (int)kv_heads, n, d, (int)splits, kind,
+                                  (float)scale, at::cuda::getCurrentCUDAStream());
+}
+
+void tree_decode_reduce(at::IntArrayRef partial_ptrs, Tensor out, double eps) {
+  TORCH_CHECK(out.is_cuda() && out.is_contiguous() && out.dim() == 3);
+  const int bh = out.size(0) * out.size(1), d = out.size(2);
+  rab::TreeReduceParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.world = (int)partial_ptrs.size();
+  TORCH_CHECK(p.world >= 1 && p.world <= rab::kMaxWorld);
+  for (int i = 0; i < p.world; ++i) p.partials[i] = reinterpret_cast<const float*>(partial_ptrs[i]);
+  p.out = out.data_ptr();
+  p.out_is_bf16 = out.scalar_type() == at::kBFloat16 ? 1 : (out.scalar_type() == at::kHalf ? 0 : 2);
+  TORCH_CHECK(p.out_is_bf16 != 2 || out.scalar_type() == at::kFloat);
+  p.eps = (float)eps;
+  c10::cuda::CUDAGuard guard(out.device());
+  rab::launch_tree_decode_reduce(p, bh, d, at::cuda::getCurrentCUDAStream());
+}
+
 void pack_kv(const Tensor& k, const Tensor& v, Tensor slot) {
   check_16bit(k, "k");
   check_16bit(v, "v");
@@ -346,6 +406,9 @@ TORCH_LIBRARY(rab, m) {
         "bool causal, int window, float scale, float softclamp, int pos_stride, int seg_len, int[] base0, int[] "
         "base1, int q_pos_offset, int[] hop_owner) -> (Tensor, Tensor)");
   m.def("pack_kv(Tensor k, Tensor v, Tensor(a!) slot) -> ()");
+  m.def("tree_decode_partial(Tensor q, Tensor? k, Tensor? v, Tensor? k_scale, Tensor? v_scale, Tensor(a!) scratch, "
+        "Tensor(b!) partial, int kv_heads, int splits, float scale) -> ()");
+  m.def("tree_decode_reduce(int[] partial_ptrs, Tensor(a!) out, float eps) -> ()");
   m.def("bwd_prep(Tensor q, Tensor o, Tensor dout, Tensor lse, Tensor(a!) qdo_buf, Tensor(b!) stat_buf, int rank) -> ()");
   m.def("attn_bwd_dq(Tensor qdo_buf, Tensor kv_buf, Tensor stat_buf, Tensor? ready, int ready_target, Tensor? "
         "kmask_bits, int batch, int heads, int kv_heads, int rank, bool causal, int window, float scale, float "
@@ -365,6 +428,7 @@ TORCH_LIBRARY_IMPL(rab, CUDA, m) {
   m.impl("umma_probe", &umma_probe);
   m.impl("attn_fwd", &attn_fwd);
   m.impl("pack_kv", &pack_kv);
+  m.impl("tree_decode_partial", &tree_decode_partial);
   m.impl("bwd_prep", &bwd_prep);
   m.impl("attn_bwd_dq", &attn_bwd_dq);
   m.impl("attn_bwd_dkdv", &attn_bwd_dkdv);
@@ -373,6 +437,7 @@ TORCH_LIBRARY_IMPL(rab, CUDA, m) {
 TORCH_LIBRARY_IMPL(rab, CompositeExplicitAutograd, m) {
   m.impl("device_barrier", &device_barrier);
   m.impl("peer_copy", &peer_copy);
+  m.impl("tree_decode_reduce", &tree_decode_reduce);
   m.impl("symm_alloc", &symm_alloc);
   m.impl("symm_open", &symm_open);
   m.impl("symm_close", &symm_close);

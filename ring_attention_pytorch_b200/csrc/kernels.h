@@ -120,6 +120,24 @@ void launch_bwd_prep(const void* q, const void* o, const void* dout, const float
                      cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
+// tree-attention decode (tree_decode_sm100.cu)
+// ------------------------------------------------------------------------------------------------
+// q [b, h, d] fp32; k, v [b*hk, n, d] (kv_kind 0 bf16, 1 fp16, 2 fp8-e4m3 with per-(b*hk) scales or null)
+// scratch [b*hk][splits][g][d+2] fp32; partial [b*h][d+2] fp32 = (out, lse*log2e, valid)
+void launch_tree_decode_partial(const float* q, const void* k, const void* v, const float* k_scale,
+                                const float* v_scale, float* scratch, float* partial, int batch, int heads,
+                                int kv_heads, int n, int d, int splits, int kv_kind, float scale,
+                                cudaStream_t stream);
+struct TreeReduceParams {
+  int world;
+  const float* partials[kMaxWorld];  // every rank's [b*h][d+2] partial (peer-mapped)
+  void* out;                         // [b*h][d]
+  int out_is_bf16;                   // 1 bf16, 0 fp16, 2 fp32
+  float eps;
+};
+void launch_tree_decode_reduce(const TreeReduceParams& p, int batch_heads, int d, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
 // misc kernels (elementwise_sm100.cu)
 // ------------------------------------------------------------------------------------------------
 // k, v [b, n, hk, d] (arbitrary batch/seq/head strides, unit d stride) -> slot [2][b*hk][n][d]
