@@ -192,3 +192,116 @@ def test_real_ring_two_gpus(layout, causal, hk):
     world = min(torch.cuda.device_count(), 8)
     world = 2 if world < 4 else 4
     run_distributed(_ring_worker, world, layout, causal, hk, backend="nccl")
+
+
+# ------------------------------------------------------------------------------------------------
+# tree-attention decode kernel
+# ------------------------------------------------------------------------------------------------
+def _dense_decode(q, k, v):
+    b, h, _, d = q.shape
+    hk = k.shape[1]
+    kx = k.float().repeat(1, h // hk, 1, 1)
+    vx = v.float().repeat(1, h // hk, 1, 1)
+    sim = torch.einsum("bhid,bhjd->bhij", q.float(), kx) * d ** -0.5
+    return torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), vx)
+
+
+@pytest.mark.parametrize("b,h,hk,n,d,dtype", [
+    (2, 8, 8, 1000, 128, torch.bfloat16),
+    (3, 8, 2, 4097, 128, torch.bfloat16),
+    (2, 16, 2, 777, 64, torch.float16),
+    (1, 4, 4, 31, 128, torch.bfloat16),
+    (4, 32, 8, 8192, 128, torch.bfloat16),
+])
+def test_tree_decode_single_gpu(b, h, hk, n, d, dtype):
+    from ring_attention_pytorch_b200 import tree_attn_decode
+
+    torch.manual_seed(0)
+    q = torch.randn(b, h, 1, d, device="cuda", dtype=dtype)
+    k = torch.randn(b, hk, n, d, device="cuda", dtype=dtype)
+    v = torch.randn(b, hk, n, d, device="cuda", dtype=dtype)
+    out = tree_attn_decode(q, k, v, shard_kv_seq=False)
+    ref = _dense_decode(q, k, v)
+    assert out.shape == (b, h, 1, d) and out.dtype == dtype
+    assert (out.float() - ref).abs().max() < 2e-2
+
+
+def test_tree_decode_fp8_kv():
+    from ring_attention_pytorch_b200.ops.tree_decode_cuda import tree_decode_cuda
+
+    torch.manual_seed(0)
+    b, h, hk, n, d = 2, 16, 4, 2048, 128
+    q = torch.randn(b, h, 1, d, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(b, hk, n, d, device="cuda")
+    v = torch.randn(b, hk, n, d, device="cuda")
+    ks = k.abs().amax(dim=(2, 3)) / 448.0
+    vs = v.abs().amax(dim=(2, 3)) / 448.0
+    k8 = (k / ks[:, :, None, None]).to(torch.float8_e4m3fn)
+    v8 = (v / vs[:, :, None, None]).to(torch.float8_e4m3fn)
+    out = tree_decode_cuda(q, k8, v8, dim_v=d, k_scale=ks.reshape(-1).contiguous(), v_scale=vs.reshape(-1).contiguous())
+    ref = _dense_decode(q, k8.float() * ks[:, :, None, None], v8.float() * vs[:, :, None, None])
+    assert (out.float() - ref).abs().max() < 3e-2
+
+
+def _tree_worker_gpu(rank, world, seq_len):
+    import torch.distributed as dist
+
+    from ring_attention_pytorch_b200 import tree_attn_decode
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda", rank)
+    q = torch.randn(2, 8, 1, 128, device=dev, dtype=torch.bfloat16)
+    k = torch.randn(2, 4, seq_len, 128, device=dev, dtype=torch.bfloat16)
+    v = torch.randn(2, 4, seq_len, 128, device=dev, dtype=torch.bfloat16)
+    ref = _dense_decode(q, k, v)
+    for _ in range(3):
+        out = tree_attn_decode(q, k, v)
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max() < 2e-2
+    dist.barrier()
+
+
+@pytest.mark.parametrize("seq_len", [4099, 1])
+def test_tree_decode_multi_gpu(seq_len):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from dist_utils import run_distributed
+
+    run_distributed(_tree_worker_gpu, 2, seq_len, backend="nccl")
+
+
+def _module_worker_gpu(rank, world, striped):
+    import torch.distributed as dist
+
+    from ring_attention_pytorch_b200 import RingTransformer
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda", rank)
+    seq_len = 1000
+    ring_seq = 512
+    kw = dict(num_tokens=256, dim=256, depth=2, causal=True, dim_head=64, heads=4, num_grouped_query_heads=2,
+              bucket_size=ring_seq)
+    ring = RingTransformer(ring_attn=True, striped_ring_attn=striped, ring_seq_size=ring_seq, use_cuda_kernel=True,
+                           **kw).to(dev)
+    dense = RingTransformer(ring_attn=False, use_cuda_kernel=False, force_regular_attn=True, **kw).to(dev)
+    dense.load_state_dict(ring.state_dict())
+    torch.manual_seed(10 + rank)
+    tokens = torch.randint(0, 256, (2, seq_len), device=dev)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        a = ring(tokens)
+        b = dense(tokens)
+    assert a.shape == b.shape
+    assert (a.float() - b.float()).abs().max() < 0.2
+    loss = ring(tokens, return_loss=True)
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(ring.token_emb.weight.grad).all()
+    dist.barrier()
+
+
+@pytest.mark.parametrize("striped", [False, True])
+def test_ring_transformer_multi_gpu(striped):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from dist_utils import run_distributed
+
+    run_distributed(_module_worker_gpu, 2, striped, backend="nccl")
