@@ -322,14 +322,40 @@ __device__ __forceinline__ void fetch_role(FwdSmem<D>& sm, const AttnFwdParams& 
 
 // ------------------------------------------------------------------------------------------------
 // warps 4-11: softmax / correction / epilogue, one thread per query row
+//
+// The 128 logits of a row are consumed as four 32-column chunks in a rolled loop (two chunks per iteration,
+// ping-pong registers): the tcgen05.ld of chunk c+1 is in flight while chunk c runs through exp2, and the
+// loop body stays small enough for the instruction cache (the fully unrolled 128-wide version spent a quarter
+// of its samples in no_instructions stalls, profiles/ncu_r1a_*).  This is an online softmax at chunk
+// granularity with a *lazy* running maximum: the maximum is only raised when a chunk exceeds it by more than
+// 2^8, in which case l, O (TMEM) and the P chunks of the current tile already written are rescaled.
 // ------------------------------------------------------------------------------------------------
-template <int D, bool BF16, int t>
-__device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams& p, uint32_t tmem) {
+template <bool BF16>
+__device__ __forceinline__ uint32_t scale_packed(uint32_t w, float f) {
+  float a, b;
+  if (BF16) {
+    a = __uint_as_float(w << 16);
+    b = __uint_as_float(w & 0xffff0000u);
+    return pack_bf16x2(a * f, b * f);
+  } else {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w);
+    a = __low2float(h);
+    b = __high2float(h);
+    return pack_f16x2(a * f, b * f);
+  }
+}
+
+template <int D, bool BF16>
+__device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams& p, const int t, uint32_t tmem) {
   const int wg_tid = threadIdx.x - (128 + 128 * t);
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
   const uint32_t s_tm = tmem + t * 128 + lane_off;
   const uint32_t o_tm = tmem + 256 + t * D + lane_off;
   const int lane = lane_id();
+  uint64_t* const s_full = &sm.s_full[0] + t;
+  uint64_t* const p_ready = &sm.p_ready[0] + t;
+  uint64_t* const o_done = &sm.o_done[0] + t;
+  uint64_t* const epi_done = &sm.epi_done[0] + t;
   uint32_t cnt = 0;
 
   const bool clamp = p.softclamp > 0.f;
@@ -341,8 +367,10 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
   for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
     Item it;
     decode_item(p, idx, it);
-    if (!it.tvalid[t]) continue;
-    const int grow = it.row0[t] + wg_tid;
+    const bool tvalid = t ? it.tvalid[1] : it.tvalid[0];
+    if (!tvalid) continue;
+    const int row0 = t ? it.row0[1] : it.row0[0];
+    const int grow = row0 + wg_tid;
     const bool row_ok = grow < p.n_q;
     const int pos_q = pos_of(p.pos, p.rank, min(grow, p.n_q - 1)) + p.q_pos_offset;
 
@@ -355,95 +383,113 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
     init_scan(scan, p, it);
     ScanTile ti;
     while (scan.next(lane, ti)) {
-      if (!ti.need[t]) continue;
-      mbar_wait(&sm.s_full[t], cnt & 1, 400 + t);
+      const bool need = t ? ti.need[1] : ti.need[0];
+      if (!need) continue;
+      const bool part = t ? ti.part[1] : ti.part[0];
+      mbar_wait(s_full, cnt & 1, 400 + t);
       tc_fence_after();
-      uint32_t sr[128];
-      tmem_ld32(s_tm + 0, sr + 0);
-      tmem_ld32(s_tm + 32, sr + 32);
-      tmem_ld32(s_tm + 64, sr + 64);
-      tmem_ld32(s_tm + 96, sr + 96);
-      tc_wait_ld();
 
-      if (clamp) {
-#pragma unroll
-        for (int j = 0; j < 128; ++j) sr[j] = __float_as_uint(fast_tanh(__uint_as_float(sr[j]) * pre) * post);
+      // per-tile mask context (only used on partial tiles)
+      const int c0 = ti.idx * BN;
+      const int split = p.pos.seg_len - c0;
+      const int a0 = p.pos.base0[ti.owner] + p.pos.stride * c0;
+      const int a1 = p.pos.base1[ti.owner] + p.pos.stride * (c0 - p.pos.seg_len);
+      const int ncols = p.n_k - c0;
+      uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu, mb2 = 0xffffffffu, mb3 = 0xffffffffu;
+      if (part && p.kmask_bits != nullptr) {
+        const uint32_t* w = p.kmask_bits + ((size_t)ti.owner * p.batch + it.b) * p.kmask_words + (size_t)ti.idx * 4;
+        mb0 = w[0]; mb1 = w[1]; mb2 = w[2]; mb3 = w[3];
       }
-      if (ti.part[t]) {
-        const int c0 = ti.idx * BN;
-        const int split = p.pos.seg_len - c0;
-        const int a0 = p.pos.base0[ti.owner] + p.pos.stride * c0;
-        const int a1 = p.pos.base1[ti.owner] + p.pos.stride * (c0 - p.pos.seg_len);
-        uint32_t mb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-        if (p.kmask_bits != nullptr) {
-          const uint32_t* w =
-              p.kmask_bits + ((size_t)ti.owner * p.batch + it.b) * p.kmask_words + (size_t)ti.idx * 4;
-          mb[0] = w[0]; mb[1] = w[1]; mb[2] = w[2]; mb[3] = w[3];
-        }
-        const int ncols = p.n_k - c0;  // columns >= ncols are beyond the end of the slot
+
+      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+
+      // one 32-column chunk: mask, lazy max, exp2, pack, store P chunk
+      auto process = [&](uint32_t (&x)[32], const int c) {
+        if (clamp) {
 #pragma unroll
-        for (int j = 0; j < 128; ++j) {
-          const int pk = (j < split ? a0 : a1) + p.pos.stride * j;
-          bool keep = (j < ncols) && ((mb[j >> 5] >> (j & 31)) & 1u);
-          if (p.causal) {
-            keep = keep && (pk <= pos_q);
-            if (p.window > 0) keep = keep && (pos_q - pk <= p.window);
+          for (int j = 0; j < 32; ++j) x[j] = __float_as_uint(fast_tanh(__uint_as_float(x[j]) * pre) * post);
+        }
+        if (part) {
+          const uint32_t mbits = c == 0 ? mb0 : (c == 1 ? mb1 : (c == 2 ? mb2 : mb3));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c * 32 + j;
+            const int pk = (col < split ? a0 : a1) + p.pos.stride * col;
+            bool keep = (col < ncols) && ((mbits >> j) & 1u);
+            if (p.causal) {
+              keep = keep && (pk <= pos_q);
+              if (p.window > 0) keep = keep && (pos_q - pk <= p.window);
+            }
+            if (!keep) x[j] = 0xff800000u;  // -inf
           }
-          if (!keep) sr[j] = 0xff800000u;  // -inf
         }
-      }
-
-      // four independent chains (ILP) instead of one 127-deep dependency chain
-      float mx4[4];
+        float m0 = fmaxf(__uint_as_float(x[0]), __uint_as_float(x[1]));
+        float m1 = fmaxf(__uint_as_float(x[2]), __uint_as_float(x[3]));
 #pragma unroll
-      for (int a = 0; a < 4; ++a) mx4[a] = __uint_as_float(sr[a]);
+        for (int j = 4; j < 32; j += 4) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(x[j]), __uint_as_float(x[j + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(x[j + 2]), __uint_as_float(x[j + 3])));
+        }
+        const float cmax = fmaxf(m0, m1) * mul;
+        if (__any_sync(0xffffffffu, cmax > m_used + 8.f)) {
+          // raise the running max (rare): rescale l, O and the P chunks of this tile written so far
+          const float m_new = fmaxf(m_used, cmax);
+          const float factor = (m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_new);
+          l *= factor;
+          ls0 *= factor; ls1 *= factor; ls2 *= factor; ls3 *= factor;
+          if (have_o) {
+            // the previous P V of this tile completed before S became visible (commit ordering)
+#pragma unroll 1
+            for (int cc = 0; cc < D; cc += 32) {
+              uint32_t orr[32];
+              tmem_ld32(o_tm + cc, orr);
+              tc_wait_ld();
 #pragma unroll
-      for (int j = 4; j < 128; j += 4) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a) mx4[a] = fmaxf(mx4[a], __uint_as_float(sr[j + a]));
-      }
-      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      mx *= mul;
-
-      // lazy rescale: only when the running max moved by more than 2^8 (warp-uniform decision)
-      const bool need_rs = mx > m_used + 8.f;
-      if (__any_sync(0xffffffffu, need_rs)) {
-        const float m_new = fmaxf(m_used, mx);
-        const float factor = (m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_new);
-        l *= factor;
-        if (have_o) {
-          // the previous P V of this tile completed before S became visible (commit ordering)
-#pragma unroll
-          for (int c = 0; c < D; c += 32) {
-            uint32_t orr[32];
-            tmem_ld32(o_tm + c, orr);
+              for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * factor);
+              tmem_st32(o_tm + cc, orr);
+            }
+          }
+#pragma unroll 1
+          for (int cc = 0; cc < c; ++cc) {
+            uint32_t pw[16];
+            tmem_ld16(s_tm + cc * 16, pw);
             tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * factor);
-            tmem_st32(o_tm + c, orr);
+            for (int i = 0; i < 16; ++i) pw[i] = scale_packed<BF16>(pw[i], factor);
+            tmem_st16(s_tm + cc * 16, pw);
           }
+          m_used = m_new;
         }
-        m_used = m_new;
-      }
-      const float m_eff = (m_used == -INFINITY) ? 0.f : m_used;
-      float lsum[8];
+        const float m_eff = (m_used == -INFINITY) ? 0.f : m_used;
+        uint32_t w16[16];
 #pragma unroll
-      for (int a = 0; a < 8; ++a) lsum[a] = 0.f;
-      uint32_t pk2[64];
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[2 * j]), mul, -m_eff));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[2 * j + 1]), mul, -m_eff));
-        lsum[(2 * j) & 7] += p0;
-        lsum[(2 * j + 1) & 7] += p1;
-        pk2[j] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+        for (int i = 0; i < 16; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(x[2 * i]), mul, -m_eff));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(x[2 * i + 1]), mul, -m_eff));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(x[2 * i + 2]), mul, -m_eff));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(x[2 * i + 3]), mul, -m_eff));
+          ls0 += p0; ls1 += p1; ls2 += p2; ls3 += p3;
+          w16[i] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+          w16[i + 1] = BF16 ? pack_bf16x2(p2, p3) : pack_f16x2(p2, p3);
+        }
+        tmem_st16(s_tm + c * 16, w16);
+      };
+
+      uint32_t xa[32], xb[32];
+      tmem_ld32(s_tm, xa);
+#pragma unroll 1
+      for (int c = 0; c < 4; c += 2) {
+        tc_wait_ld();                      // chunk c has landed
+        tmem_ld32(s_tm + (c + 1) * 32, xb);  // chunk c+1 in flight during the math of chunk c
+        process(xa, c);
+        tc_wait_ld();                      // chunk c+1 has landed
+        if (c + 2 < 4) tmem_ld32(s_tm + (c + 2) * 32, xa);
+        process(xb, c + 1);
       }
-      l += ((lsum[0] + lsum[1]) + (lsum[2] + lsum[3])) + ((lsum[4] + lsum[5]) + (lsum[6] + lsum[7]));
-      tmem_st32(s_tm + 0, pk2);
-      tmem_st32(s_tm + 32, pk2 + 32);
+      l += (ls0 + ls1) + (ls2 + ls3);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&sm.p_ready[t]);
+      mbar_arrive(p_ready);
       cnt++;
       cnt_item++;
       have_o = true;
@@ -451,13 +497,13 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
 
     // epilogue: O / l -> 16 bit, lse
     if (cnt_item > 0) {
-      mbar_wait(&sm.o_done[t], (cnt - 1) & 1, 410 + t);
+      mbar_wait(o_done, (cnt - 1) & 1, 410 + t);
       tc_fence_after();
     }
     const float inv = l > 0.f ? 1.f / l : 0.f;
     uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
                                            (((size_t)it.b * p.n_q + (row_ok ? grow : 0)) * p.heads + it.h) * D);
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < D; c += 32) {
       uint32_t orr[32];
       if (cnt_item > 0) {
@@ -483,7 +529,7 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
       p.lse[((size_t)it.b * p.heads + it.h) * p.n_q + grow] = l > 0.f ? (m_eff + log2f(l)) * kLn2 : INFINITY;
     }
     tc_fence_before();
-    mbar_arrive(&sm.epi_done[t]);
+    mbar_arrive(epi_done);
   }
 }
 
@@ -536,11 +582,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
   } else {
     setmaxnreg_inc<216>();
-    if (warp < 8) {
-      softmax_role<D, BF16, 0>(sm, p, tmem);
-    } else {
-      softmax_role<D, BF16, 1>(sm, p, tmem);
-    }
+    softmax_role<D, BF16>(sm, p, warp < 8 ? 0 : 1, tmem);
   }
 
   tc_fence_before();
