@@ -144,7 +144,7 @@ def test_graft_smoke():
 # ------------------------------------------------------------------------------------------------
 # real multi-GPU ring (NVLink, symmetric memory) – needs >= 2 devices
 # ------------------------------------------------------------------------------------------------
-def _ring_worker(rank, world, layout, causal, hk):
+def _ring_worker(rank, world, layout, causal, hk, kmask=False):
     import torch.distributed as dist
 
     from ring_attention_pytorch_b200.ops.oracle import attention_with_positions
@@ -159,9 +159,10 @@ def _ring_worker(rank, world, layout, causal, hk):
     vs = [torch.randn(b, n, hk, d, device=dev, dtype=torch.bfloat16) for _ in range(world)]
     gs = [torch.randn(b, n, h, d, device=dev, dtype=torch.bfloat16) for _ in range(world)]
     q, k, v = (t[rank].clone().requires_grad_() for t in (qs, ks, vs))
+    masks = [torch.rand(b, n, device=dev) > 0.3 for _ in range(world)] if kmask else None
     for _ in range(2):  # twice: exercises the double-buffered staging + epoch barrier
-        out = ring_flash_attn_cuda(q, k, v, None, causal, 1024, True, layout == "striped", None, world, False, 50.0,
-                                   layout)
+        out = ring_flash_attn_cuda(q, k, v, masks[rank] if kmask else None, causal, 1024, True, layout == "striped",
+                                   None, world, False, 50.0, layout)
         dq, dk, dv = torch.autograd.grad(out, (q, k, v), gs[rank])
     torch.cuda.synchronize()
     pm = make_position_map(layout, world, n)
@@ -173,7 +174,8 @@ def _ring_worker(rank, world, layout, causal, hk):
     loss = 0
     outs = []
     for r in range(world):
-        o = attention_with_positions(qf[r], k_all, v_all, pm.positions(r, dev), k_pos, causal=causal)
+        o = attention_with_positions(qf[r], k_all, v_all, pm.positions(r, dev), k_pos, causal=causal,
+                                     key_mask=torch.cat(masks, 1) if kmask else None)
         outs.append(o)
         loss = loss + (o * gs[r].float()).sum()
     loss.backward()
@@ -183,15 +185,16 @@ def _ring_worker(rank, world, layout, causal, hk):
     dist.barrier()
 
 
-@pytest.mark.parametrize("layout,causal,hk", [("plain", False, 4), ("striped", True, 2), ("zigzag", True, 4)])
-def test_real_ring_two_gpus(layout, causal, hk):
+@pytest.mark.parametrize("layout,causal,hk,kmask", [("plain", False, 4, False), ("striped", True, 2, False),
+                                                    ("zigzag", True, 4, False), ("plain", False, 2, True)])
+def test_real_ring_two_gpus(layout, causal, hk, kmask):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     from dist_utils import run_distributed
 
     world = min(torch.cuda.device_count(), 8)
     world = 2 if world < 4 else 4
-    run_distributed(_ring_worker, world, layout, causal, hk, backend="nccl")
+    run_distributed(_ring_worker, world, layout, causal, hk, kmask, backend="nccl")
 
 
 # ------------------------------------------------------------------------------------------------
