@@ -78,6 +78,12 @@ __device__ __forceinline__ size_t kv_elem_bytes() {
 
 // q: [b, h, d] (fp32 staged by the host wrapper), k: [b*hk, n, d], v: [b*hk, n, dv]
 // scratch: [b*hk][splits][g][dv + 2]  (acc..., m, l) in the log2 domain
+//
+// Per 64-key tile:   scores : 8 lanes per key, 4 keys per warp step, all 16-byte loads of the tile issued up
+//                             front (memory-level parallelism), q held in registers, 3-step shuffle reduce
+//                    softmax: warp gi owns head gi (online, log2 domain)
+//                    P V    : thread = (key group of 8, 8-column chunk); the 8 V loads of a tile are issued
+//                             before the FMAs; probabilities are broadcast from smem as one float4 per key
 template <int D, int KV_KIND>
 __global__ void __launch_bounds__(TD_THREADS)
 tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__ k, const void* __restrict__ v,
@@ -94,83 +100,78 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
   const int k0 = split * per, k1 = min(n, k0 + per);
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
-  __shared__ float q_s[TD_MAX_G][D];
-  __shared__ float s_s[TD_MAX_G][TD_TILE];
+  __shared__ __align__(16) float s_s[TD_TILE][TD_MAX_G];  // scores, then probabilities: one float4 per key
   __shared__ float corr_s[TD_MAX_G];
   __shared__ float red_s[8][TD_MAX_G][D + 1];
 
   const float ks = k_scale ? k_scale[bhk] : 1.f;
   const float vs = v_scale ? v_scale[bhk] : 1.f;
-  for (int i = tid; i < g * D; i += TD_THREADS) {
-    const int gi = i / D, c = i % D;
-    // query head j uses kv head j % kv_heads  ->  heads {kvh, kvh + hk, ...}
-    q_s[gi][c] = q[((size_t)b * heads + (g0 + gi) * kv_heads + kvh) * D + c] * scale_log2 * ks;
-  }
-  __syncthreads();
 
-  // PV ownership: thread -> (key group kgrp of 8, column chunk of 8 elements)
-  constexpr int CHUNKS = D / 8;              // 16 for D=128, 8 for D=64
+  // QK ownership: 8 lanes per key (each lane D/8 elements), 4 keys per warp step, 16 keys per warp per tile
+  constexpr int EPL = D / 8;  // elements per lane: 16 (D=128) or 8 (D=64)
+  const int sub = lane / 8, l8 = lane % 8;
+  float qr[TD_MAX_G][EPL];
+#pragma unroll
+  for (int gi = 0; gi < TD_MAX_G; ++gi) {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      // query head j uses kv head j % kv_heads  ->  heads {kvh, kvh + hk, ...}
+      qr[gi][e] = gi < g ? q[((size_t)b * heads + (g0 + gi) * kv_heads + kvh) * D + l8 * EPL + e] * scale_log2 * ks
+                         : 0.f;
+    }
+  }
+
+  // PV ownership: thread -> (key group kgrp, column chunk of 8 elements)
+  constexpr int CHUNKS = D / 8;                 // 16 for D=128, 8 for D=64
   constexpr int KGROUPS = TD_THREADS / CHUNKS;  // 8 or 16
+  constexpr int KPT = TD_TILE / KGROUPS;        // keys per thread per tile: 8 or 4
   const int chunk = tid % CHUNKS, kgrp = tid / CHUNKS;
   float acc[TD_MAX_G][8];
 #pragma unroll
   for (int gi = 0; gi < TD_MAX_G; ++gi)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[gi][e] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;  // meaningful in threads tid < g (one softmax owner per head)
+  float m_run = -INFINITY, l_run = 0.f;  // warp gi keeps the running stats of head gi (identical in all lanes)
 
   const size_t eb = kv_elem_bytes<KV_KIND>();
   const uint8_t* kbase = reinterpret_cast<const uint8_t*>(k) + (size_t)bhk * n * D * eb;
   const uint8_t* vbase = reinterpret_cast<const uint8_t*>(v) + (size_t)bhk * n * D * eb;
 
-  // QK ownership: 8 lanes per key (each lane D/8 elements), 4 keys per warp step, 16 keys per warp per tile
-  constexpr int EPL = D / 8;  // elements per lane: 16 (D=128) or 8 (D=64)
-  const int sub = lane / 8, l8 = lane % 8;
-
   for (int t0 = k0; t0 < k1; t0 += TD_TILE) {
     // ---- scores -------------------------------------------------------------------------------
+    float kf[4][EPL];
 #pragma unroll
     for (int step = 0; step < 4; ++step) {
-      const int kl = warp * 16 + step * 4 + sub;  // key within tile
-      const int key = t0 + kl;
+      const int key = min(t0 + warp * 16 + step * 4 + sub, k1 - 1);  // clamp: loads stay in bounds
+      const uint8_t* row = kbase + ((size_t)key * D + l8 * EPL) * eb;
+#pragma unroll
+      for (int c = 0; c < EPL; c += 8) KvTraits<KV_KIND>::load8(row + c * eb, &kf[step][c]);
+    }
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+      const int kl = warp * 16 + step * 4 + sub;
+      const bool live = (t0 + kl) < k1;
       float part[TD_MAX_G];
 #pragma unroll
-      for (int gi = 0; gi < TD_MAX_G; ++gi) part[gi] = 0.f;
-      if (key < k1) {
-        const uint8_t* row = kbase + ((size_t)key * D + l8 * EPL) * eb;
-#pragma unroll
-        for (int c = 0; c < EPL; c += 8) {
-          float kv8[8];
-          KvTraits<KV_KIND>::load8(row + c * eb, kv8);
-#pragma unroll
-          for (int gi = 0; gi < TD_MAX_G; ++gi) {
-            if (gi < g) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) part[gi] = fmaf(kv8[e], q_s[gi][l8 * EPL + c + e], part[gi]);
-            }
-          }
-        }
-      }
-#pragma unroll
       for (int gi = 0; gi < TD_MAX_G; ++gi) {
-        if (gi < g) {
-          float x = part[gi];
-          x += __shfl_xor_sync(0xffffffffu, x, 1);
-          x += __shfl_xor_sync(0xffffffffu, x, 2);
-          x += __shfl_xor_sync(0xffffffffu, x, 4);
-          if (l8 == 0) s_s[gi][kl] = key < k1 ? x : -INFINITY;
-        }
+        float a = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) a = fmaf(kf[step][e], qr[gi][e], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        part[gi] = live ? a : -INFINITY;
       }
+      if (l8 == 0) *reinterpret_cast<float4*>(&s_s[kl][0]) = make_float4(part[0], part[1], part[2], part[3]);
     }
     __syncthreads();
-    // ---- online softmax: warp gi owns head gi (all its lanes keep identical running stats) ----------
+    // ---- online softmax: warp gi owns head gi -------------------------------------------------------
     if (warp < g) {
       const int gi = warp;
-      const float a = s_s[gi][lane], bb = s_s[gi][lane + 32];
+      const float a = s_s[lane][gi], bb = s_s[lane + 32][gi];
       float mx = fmaxf(a, bb);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      // all lanes keep identical running stats for their head
       const float m_prev = m_run, l_prev = l_run;
       const float m_new = fmaxf(m_prev, mx);
       const float m_eff = m_new == -INFINITY ? 0.f : m_new;
@@ -179,34 +180,40 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       const float corr = m_prev == -INFINITY ? 0.f : fast_exp2(m_prev - m_eff);
-      s_s[gi][lane] = pa;
-      s_s[gi][lane + 32] = pb;
+      s_s[lane][gi] = pa;
+      s_s[lane + 32][gi] = pb;
       m_run = m_new;
       l_run = l_prev * corr + sum;
       if (lane == 0) corr_s[gi] = corr;
+    } else if (warp < TD_MAX_G) {
+      // unused head slots must read as zero probability in the float4 broadcast below
+      s_s[lane][warp] = 0.f;
+      s_s[lane + 32][warp] = 0.f;
+      if (lane == 0) corr_s[warp] = 0.f;
     }
     __syncthreads();
     // ---- P V --------------------------------------------------------------------------------------
+    float vf[KPT][8];
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+      const int key = min(t0 + kgrp + i * KGROUPS, k1 - 1);
+      KvTraits<KV_KIND>::load8(vbase + ((size_t)key * D + chunk * 8) * eb, vf[i]);
+    }
 #pragma unroll
     for (int gi = 0; gi < TD_MAX_G; ++gi) {
-      if (gi < g) {
-        const float c = corr_s[gi];
+      const float c = corr_s[gi];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[gi][e] *= c;
-      }
+      for (int e = 0; e < 8; ++e) acc[gi][e] *= c;
     }
-    for (int kl = kgrp; kl < TD_TILE; kl += KGROUPS) {
-      const int key = t0 + kl;
-      if (key >= k1) break;
-      float v8[8];
-      KvTraits<KV_KIND>::load8(vbase + ((size_t)key * D + chunk * 8) * eb, v8);
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+      const int kl = kgrp + i * KGROUPS;
+      const float4 p4 = *reinterpret_cast<const float4*>(&s_s[kl][0]);  // 0 for keys beyond the shard
+      const float pk[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
       for (int gi = 0; gi < TD_MAX_G; ++gi) {
-        if (gi < g) {
-          const float pk = s_s[gi][kl];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[gi][e] = fmaf(pk, v8[e], acc[gi][e]);
-        }
+        for (int e = 0; e < 8; ++e) acc[gi][e] = fmaf(pk[gi], vf[i][e], acc[gi][e]);
       }
     }
     __syncthreads();
@@ -232,10 +239,10 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
   }
   for (int i = tid; i < g * D; i += TD_THREADS) {
     const int gi = i / D, c = i % D;
-    float s = 0.f;
+    float sacc = 0.f;
 #pragma unroll
-    for (int kg = 0; kg < 8; ++kg) s += red_s[kg][gi][c];
-    out[gi * (D + 2) + c] = s * vs;
+    for (int kg = 0; kg < 8; ++kg) sacc += red_s[kg][gi][c];
+    out[gi * (D + 2) + c] = sacc * vs;
   }
   if (warp < g && lane == 0) {
     out[warp * (D + 2) + D] = m_run;

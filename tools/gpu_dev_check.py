@@ -241,6 +241,39 @@ def case_perf_bwd(n=16384, h=16, d=128, causal=True, iters=5, b=1, hk=None):
     return res
 
 
+def case_perf_decode(batch=256, h=32, hk=8, n=8192, d=128, fp8=False, iters=20):
+    import torch
+    from ring_attention_pytorch_b200.ops.tree_decode_cuda import tree_decode_cuda
+
+    q = torch.randn(batch, h, 1, d, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(batch, hk, n, d, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(batch, hk, n, d, device="cuda", dtype=torch.bfloat16)
+    ks = vs = None
+    if fp8:
+        k, v = k.to(torch.float8_e4m3fn), v.to(torch.float8_e4m3fn)
+        ks = torch.ones(batch * hk, device="cuda")
+        vs = torch.ones(batch * hk, device="cuda")
+    for _ in range(3):
+        out = tree_decode_cuda(q, k, v, dim_v=d, k_scale=ks, v_scale=vs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        out = tree_decode_cuda(q, k, v, dim_v=d, k_scale=ks, v_scale=vs)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    kv_bytes = 2 * k.numel() * k.element_size()
+    # correctness spot check on a slice
+    kx = k[:2].float().repeat(1, h // hk, 1, 1)
+    vx = v[:2].float().repeat(1, h // hk, 1, 1)
+    sim = torch.einsum("bhid,bhjd->bhij", q[:2].float(), kx) * d ** -0.5
+    ref = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), vx)
+    err = (out[:2].float() - ref).abs().max().item()
+    return {"ms": ms, "kv_gb_per_s": kv_bytes / ms / 1e6, "hbm_frac_of_6585": kv_bytes / ms / 1e6 / 6585.0, "err": err,
+            "ok": err < 3e-2}
+
+
 def case_perf(n=16384, h=16, d=128, causal=True, iters=5, b=1, hk=None):
     import torch
     from ring_attention_pytorch_b200.ops import _ext
@@ -356,6 +389,9 @@ CASES = {
     "perfbwd_causal_16k": lambda: case_perf_bwd(),
     "perfbwd_full_8k": lambda: case_perf_bwd(n=8192, causal=False),
     "perfbwd_causal_64k_h8": lambda: case_perf_bwd(n=65536, h=8, iters=3),
+    "perfdec_bf16": lambda: case_perf_decode(),
+    "perfdec_fp8": lambda: case_perf_decode(fp8=True),
+    "perfdec_mha_b32": lambda: case_perf_decode(batch=32, h=32, hk=32, n=8192),
     "perf_causal_16k": lambda: case_perf(),
     "perf_full_8k": lambda: case_perf(n=8192, causal=False),
     "perf_causal_64k_h8": lambda: case_perf(n=65536, h=8, iters=3),
@@ -369,6 +405,7 @@ GROUPS = {
     "bwd": [c for c in CASES if c.startswith("bwd")],
     "rbwd": [c for c in CASES if c.startswith("rbwd")],
     "perfbwd": [c for c in CASES if c.startswith("perfbwd")],
+    "perfdec": [c for c in CASES if c.startswith("perfdec")],
     "perf": [c for c in CASES if c.startswith("perf_")],
 }
 
