@@ -291,8 +291,8 @@ __device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, ui
   }
 }
 
-template <int D, bool BF16, int W>
-__device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem) {
+template <int D, bool BF16>
+__device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem) {
   const int wg_tid = threadIdx.x - (128 + 128 * W);
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
   const uint32_t x_tm = tmem + W * 128 + lane_off;
@@ -325,7 +325,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
     uint32_t jj = 0;
     while (scan.next(lane, t)) {
       if (((jj++) & 1u) != (uint32_t)W) continue;
-      mbar_wait(&sm.s_full[W], cnt & 1, 700 + W);
+      mbar_wait((&sm.s_full[0] + W), cnt & 1, 700 + W);
       tc_fence_after();
       uint32_t sr[128];
       tmem_ld32(x_tm + 0, sr + 0);
@@ -334,7 +334,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
       tmem_ld32(x_tm + 96, sr + 96);
       tc_wait_ld();
       tc_fence_before();
-      mbar_arrive(&sm.s_taken[W]);
+      mbar_arrive((&sm.s_taken[0] + W));
 
       if (t.part[0]) {
         const int c0 = t.idx * 128;
@@ -359,26 +359,45 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
         }
       }
 
-      mbar_wait(&sm.dp_full[W], cnt & 1, 710 + W);
-      tc_fence_after();
-      // dS = P o (dP - delta) [* (1 - tanh^2) with softclamp]; the softmax scale is folded into the epilogue.
-      // Masked logits are -inf, so exp2 already yields P = 0 on the plain path.
+      // P = exp2(S*c - lse) while the tensor core is busy with dP = dO V^T of this tile (masked logits are
+      // -inf and give exactly 0)
       if (!clamp) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t dp[32];
-          tmem_ld32(x_tm + c * 32, dp);
-          tc_wait_ld();
-          uint32_t w16[16];
+        for (int j = 0; j < 128; ++j) sr[j] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(sr[j]), mul, -lse2)));
+      }
+      mbar_wait((&sm.dp_full[0] + W), cnt & 1, 710 + W);
+      tc_fence_after();
+      // dS = P o (dP - delta) [* (1 - tanh^2) with softclamp]; the softmax scale is folded into the epilogue.
+      if (!clamp) {
+        uint32_t dpa[32], dpb[32];
+        tmem_ld32(x_tm, dpa);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c * 32 + 2 * i]), mul, -lse2));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c * 32 + 2 * i + 1]), mul, -lse2));
-            const float d0 = p0 * (__uint_as_float(dp[2 * i]) - delta);
-            const float d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - delta);
-            w16[i] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
+        for (int c = 0; c < 4; c += 2) {
+          tc_wait_ld();
+          tmem_ld32(x_tm + (c + 1) * 32, dpb);  // next chunk in flight during the math of this one
+          {
+            uint32_t w16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float d0 = __uint_as_float(sr[c * 32 + 2 * i]) * (__uint_as_float(dpa[2 * i]) - delta);
+              const float d1 = __uint_as_float(sr[c * 32 + 2 * i + 1]) * (__uint_as_float(dpa[2 * i + 1]) - delta);
+              w16[i] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
+            }
+            tc_wait_ld();  // chunk c+1 must have left TMEM before its columns are reused below
+            if (c + 2 < 4) tmem_ld32(x_tm + (c + 2) * 32, dpa);
+            tmem_st16(x_tm + c * 16, w16);
           }
-          tmem_st16(x_tm + c * 16, w16);
+          {
+            uint32_t w16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float d0 = __uint_as_float(sr[(c + 1) * 32 + 2 * i]) * (__uint_as_float(dpb[2 * i]) - delta);
+              const float d1 =
+                  __uint_as_float(sr[(c + 1) * 32 + 2 * i + 1]) * (__uint_as_float(dpb[2 * i + 1]) - delta);
+              w16[i] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
+            }
+            tmem_st16(x_tm + (c + 1) * 16, w16);
+          }
         }
       } else {
 #pragma unroll 1
@@ -410,7 +429,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
       }
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&sm.ds_ready[W]);
+      mbar_arrive((&sm.ds_ready[0] + W));
       cnt++;
     }
 
@@ -490,11 +509,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_cons
     if (warp == 1) dq_mma<D, BF16>(sm, p, tmem);
   } else {
     setmaxnreg_inc<216>();
-    if (warp < 8) {
-      dq_softmax<D, BF16, 0>(sm, p, tmem);
-    } else {
-      dq_softmax<D, BF16, 1>(sm, p, tmem);
-    }
+    dq_softmax<D, BF16>(sm, p, warp < 8 ? 0 : 1, tmem);
   }
   tc_fence_before();
   __syncthreads();
@@ -504,7 +519,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_cons
 // =================================================================================================
 // dK/dV kernel
 // =================================================================================================
-constexpr int QSTAGES = 3;
+constexpr int QSTAGES = 4;
 
 template <int D>
 struct DkvSmem {
@@ -709,8 +724,8 @@ __device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, 
   }
 }
 
-template <int D, bool BF16, int W>
-__device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem) {
+template <int D, bool BF16>
+__device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem) {
   const int wg_tid = threadIdx.x - (128 + 128 * W);
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
   const uint32_t st_tm = tmem + W * 128 + lane_off;
@@ -743,14 +758,14 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
       const uint32_t jj = jn++;
       if ((jj & 1u) != (uint32_t)W) continue;
       const uint32_t stg = (tile_base + jj) % QSTAGES;
-      mbar_wait(&sm.sdp_full[W], cnt & 1, 1000 + W);
+      mbar_wait((&sm.sdp_full[0] + W), cnt & 1, 1000 + W);
       tc_fence_after();
       uint32_t sr[64], dp[64];
       tmem_ld32(st_tm + 0, sr + 0);
       tmem_ld32(st_tm + 32, sr + 32);
-      tmem_ld32(dpt_tm + 0, dp + 0);
-      tmem_ld32(dpt_tm + 32, dp + 32);
       tc_wait_ld();
+      tmem_ld32(dpt_tm + 0, dp + 0);  // dP^T stays in flight while the exponentials below run
+      tmem_ld32(dpt_tm + 32, dp + 32);
 
       const int c0 = t.idx * 64;
       const float4* l4 = reinterpret_cast<const float4*>(sm.lse2[stg]);
@@ -763,21 +778,30 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
 #pragma unroll
         for (int q4 = 0; q4 < 16; ++q4) {
           const float4 lv = l4[q4];
-          const float4 dv = d4[q4];
           const float p0 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 0]), mul, -lv.x));
           const float p1 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 1]), mul, -lv.y));
           const float p2 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 2]), mul, -lv.z));
           const float p3 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 3]), mul, -lv.w));
-          const float e0 = p0 * (__uint_as_float(dp[q4 * 4 + 0]) - dv.x);
-          const float e1 = p1 * (__uint_as_float(dp[q4 * 4 + 1]) - dv.y);
-          const float e2 = p2 * (__uint_as_float(dp[q4 * 4 + 2]) - dv.z);
-          const float e3 = p3 * (__uint_as_float(dp[q4 * 4 + 3]) - dv.w);
+          sr[q4 * 4 + 0] = __float_as_uint(p0);
+          sr[q4 * 4 + 1] = __float_as_uint(p1);
+          sr[q4 * 4 + 2] = __float_as_uint(p2);
+          sr[q4 * 4 + 3] = __float_as_uint(p3);
           pw[q4 * 2] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
           pw[q4 * 2 + 1] = BF16 ? pack_bf16x2(p2, p3) : pack_f16x2(p2, p3);
+        }
+        tc_wait_ld();  // dP^T has landed
+#pragma unroll
+        for (int q4 = 0; q4 < 16; ++q4) {
+          const float4 dv = d4[q4];
+          const float e0 = __uint_as_float(sr[q4 * 4 + 0]) * (__uint_as_float(dp[q4 * 4 + 0]) - dv.x);
+          const float e1 = __uint_as_float(sr[q4 * 4 + 1]) * (__uint_as_float(dp[q4 * 4 + 1]) - dv.y);
+          const float e2 = __uint_as_float(sr[q4 * 4 + 2]) * (__uint_as_float(dp[q4 * 4 + 2]) - dv.z);
+          const float e3 = __uint_as_float(sr[q4 * 4 + 3]) * (__uint_as_float(dp[q4 * 4 + 3]) - dv.w);
           dw[q4 * 2] = BF16 ? pack_bf16x2(e0, e1) : pack_f16x2(e0, e1);
           dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(e2, e3) : pack_f16x2(e2, e3);
         }
       } else {
+        tc_wait_ld();  // dP^T has landed
         const int split = p.pos.seg_len - c0;
         const int a0 = p.pos.base0[t.owner] + p.pos.stride * c0 + p.q_pos_offset;
         const int a1 = p.pos.base1[t.owner] + p.pos.stride * (c0 - p.pos.seg_len) + p.q_pos_offset;
@@ -825,7 +849,7 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
       tmem_st32(dpt_tm, dw);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&sm.pds_ready[W]);
+      mbar_arrive((&sm.pds_ready[0] + W));
       cnt++;
     }
     tile_base += jn;  // both warpgroups walk the whole sequence, so the stage ring stays in step
@@ -904,11 +928,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
     if (warp == 1) dkv_mma<D, BF16>(sm, p, tmem);
   } else {
     setmaxnreg_inc<216>();
-    if (warp < 8) {
-      dkv_softmax<D, BF16, 0>(sm, p, tmem);
-    } else {
-      dkv_softmax<D, BF16, 1>(sm, p, tmem);
-    }
+    dkv_softmax<D, BF16>(sm, p, warp < 8 ? 0 : 1, tmem);
   }
   tc_fence_before();
   __syncthreads();
