@@ -192,14 +192,16 @@ __device__ __forceinline__ void dq_producer(DqSmem<D>& sm, const AttnBwdParams& 
 }
 
 template <int D, bool BF16>
-__device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem) {
+__device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0, BF16 ? 1 : 0);   // S, dP : N = 128 keys
   constexpr uint32_t idesc_dq = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);    // dQ    : N = D, B MN-major
   constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
   constexpr uint64_t mnmaj = umma_smem_desc_hi_lo(SUB128, 1024, UMMA_LAYOUT_SW128);
+  // whole warp in lock step with warp-uniform operands; the *_w wrappers elect the issuing lane
+  const int lane = lane_id();
+  const uint32_t tmem = warp_uniform(tmem_in);
   const uint32_t x_tm[2] = {tmem + 0, tmem + 128};
   const uint32_t dq_tm = tmem + 256;
-  const int lane = lane_id();
 
   uint32_t n_item = 0, tile_base = 0;
   uint32_t cnt[2] = {0, 0};  // tiles completed per stream (global) -> barrier parities
@@ -207,11 +209,8 @@ __device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, ui
   for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
     DqItem it;
     dq_decode(p, idx, it);
-    if (lane == 0) {
-      mbar_wait(&sm.qdo_full, n_item & 1, 600);
-      tc_fence_after();
-    }
-    __syncwarp();
+    mbar_wait(&sm.qdo_full, n_item & 1, 600);
+    tc_fence_after();
 
     StreamFeeder<DqScan> feed;
     dq_init_scan(feed.scan, p, it);
@@ -220,7 +219,11 @@ __device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, ui
     uint32_t jj[2] = {0, 0};
     bool dq_started = false;
     uint32_t ntiles = 0;
-    const uint32_t qa = smem_u32(sm.q), da = smem_u32(sm.dout);
+    // descriptor bases (warp-uniform); per-MMA work is one constant add per operand
+    const uint64_t q_desc = umma_desc(kmaj, smem_u32(sm.q)), do_desc = umma_desc(kmaj, smem_u32(sm.dout));
+    const uint64_t k_kdesc0 = umma_desc(kmaj, smem_u32(sm.k[0])), k_mndesc0 = umma_desc(mnmaj, smem_u32(sm.k[0]));
+    const uint64_t v_kdesc0 = umma_desc(kmaj, smem_u32(sm.v[0]));
+    constexpr uint32_t SLOT16 = DqSmem<D>::TILE >> 4;
     while (state[0] != 3 || state[1] != 3) {
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
@@ -233,47 +236,40 @@ __device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, ui
         }
         const uint32_t g = tile_base + jj[w];
         const uint32_t ks = g % 3, kph = (g / 3) & 1, vs = g % 2, vph = (g / 2) & 1;
+        const uint64_t kd = k_kdesc0 + uint64_t(ks * SLOT16), kmn = k_mndesc0 + uint64_t(ks * SLOT16);
+        const uint64_t vd = v_kdesc0 + uint64_t(vs * SLOT16);
         if (state[w] == 0) {
           if (!warp_test(&sm.k_full[ks], kph, lane)) continue;
-          if (lane == 0) {
-            tc_fence_after();
-            const uint32_t ka = smem_u32(sm.k[ks]);
+          tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-              const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
-              umma_ss(x_tm[w], umma_desc(kmaj, qa + off), umma_desc(kmaj, ka + off), idesc_s, kk > 0);
-            }
-            umma_commit(&sm.s_full[w]);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
+            umma_ss_w(x_tm[w], umma_desc_add(q_desc, off), umma_desc_add(kd, off), idesc_s, kk > 0);
           }
+          umma_commit_w(&sm.s_full[w]);
           state[w] = 1;
         } else if (state[w] == 1) {
           if (!warp_test(&sm.v_full[vs], vph, lane)) continue;
           if (!warp_test(&sm.s_taken[w], cnt[w] & 1, lane)) continue;
-          if (lane == 0) {
-            tc_fence_after();
-            const uint32_t va = smem_u32(sm.v[vs]);
+          tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-              const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
-              umma_ss(x_tm[w], umma_desc(kmaj, da + off), umma_desc(kmaj, va + off), idesc_s, kk > 0);
-            }
-            umma_commit(&sm.dp_full[w]);
-            umma_commit(&sm.v_empty[vs]);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
+            umma_ss_w(x_tm[w], umma_desc_add(do_desc, off), umma_desc_add(vd, off), idesc_s, kk > 0);
           }
+          umma_commit_w(&sm.dp_full[w]);
+          umma_commit_w(&sm.v_empty[vs]);
           state[w] = 2;
         } else {
           if (!warp_test(&sm.ds_ready[w], cnt[w] & 1, lane)) continue;
-          if (lane == 0) {
-            if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 610);
-            tc_fence_after();
-            const uint32_t ka = smem_u32(sm.k[ks]);
+          if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 610);
+          tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < 128 / 16; ++kk) {
-              umma_ts(dq_tm, x_tm[w] + kk * 8, umma_desc(mnmaj, ka + kk * 2048), idesc_dq,
+          for (int kk = 0; kk < 128 / 16; ++kk) {
+            umma_ts_w(dq_tm, x_tm[w] + kk * 8, umma_desc_add(kmn, kk * 2048), idesc_dq,
                       (dq_started || kk > 0) ? 1u : 0u);
-            }
-            umma_commit(&sm.k_empty[ks]);
           }
+          umma_commit_w(&sm.k_empty[ks]);
           dq_started = true;
           cnt[w]++;
           ntiles++;
@@ -281,13 +277,10 @@ __device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, ui
         }
       }
     }
-    if (lane == 0) {
-      if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 611);
-      umma_commit(&sm.dq_done);
-      umma_commit(&sm.qdo_empty);
-    }
+    if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 611);
+    umma_commit_w(&sm.dq_done);
+    umma_commit_w(&sm.qdo_empty);
     tile_base += ntiles;
-    __syncwarp();
   }
 }
 
@@ -627,16 +620,17 @@ __device__ __forceinline__ void dkv_producer(DkvSmem<D>& sm, const AttnBwdParams
 }
 
 template <int D, bool BF16>
-__device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem) {
+__device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);   // S^T, dP^T : N = 64 queries
   constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);  // dV, dK    : N = D, B MN-major
   constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
   constexpr uint64_t mnmaj64 = umma_smem_desc_hi_lo(SUB64, 1024, UMMA_LAYOUT_SW128);
   // TMEM: stream w: S^T at w*128 (P^T aliases its first 32 columns), dP^T at w*128+64 (dS^T aliases it)
+  const int lane = lane_id();
+  const uint32_t tmem = warp_uniform(tmem_in);
   const uint32_t st_tm[2] = {tmem + 0, tmem + 128};
   const uint32_t dpt_tm[2] = {tmem + 64, tmem + 192};
   const uint32_t dk_tm = tmem + 256, dv_tm = tmem + 256 + D;
-  const int lane = lane_id();
 
   uint32_t n_item = 0, tile_base = 0;
   uint32_t cnt[2] = {0, 0};
@@ -644,11 +638,8 @@ __device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, 
   for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
     DkvItem it;
     dkv_decode(p, idx, it);
-    if (lane == 0) {
-      mbar_wait(&sm.kv_full, n_item & 1, 900);
-      tc_fence_after();
-    }
-    __syncwarp();
+    mbar_wait(&sm.kv_full, n_item & 1, 900);
+    tc_fence_after();
 
     StreamFeeder<DkvScan> feed;
     dkv_init_scan(feed.scan, p, it);
@@ -657,7 +648,11 @@ __device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, 
     uint32_t jj[2] = {0, 0};
     bool acc_started = false;
     uint32_t ntiles = 0;
-    const uint32_t ka = smem_u32(sm.k), va = smem_u32(sm.v);
+    const uint64_t k_desc = umma_desc(kmaj, smem_u32(sm.k)), v_desc = umma_desc(kmaj, smem_u32(sm.v));
+    const uint64_t q_kdesc0 = umma_desc(kmaj, smem_u32(sm.q[0])), q_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.q[0]));
+    const uint64_t do_kdesc0 = umma_desc(kmaj, smem_u32(sm.dout[0])),
+                   do_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.dout[0]));
+    constexpr uint32_t STAGE16 = DkvSmem<D>::Q_TILE >> 4;
     while (state[0] != 3 || state[1] != 3) {
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
@@ -670,43 +665,40 @@ __device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, 
         }
         const uint32_t g = tile_base + jj[w];
         const uint32_t st = g % QSTAGES, ph = (g / QSTAGES) & 1;
-        const uint32_t qa = smem_u32(sm.q[st]), da = smem_u32(sm.dout[st]);
+        const uint64_t qk = q_kdesc0 + uint64_t(st * STAGE16), qmn = q_mndesc0 + uint64_t(st * STAGE16);
+        const uint64_t dok = do_kdesc0 + uint64_t(st * STAGE16), domn = do_mndesc0 + uint64_t(st * STAGE16);
         if (state[w] == 0) {
           if (!warp_test(&sm.qd_full[st], ph, lane)) continue;
-          if (lane == 0) {
-            tc_fence_after();
+          tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-              const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
-              const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
-              umma_ss(st_tm[w], umma_desc(kmaj, ka + offk), umma_desc(kmaj, qa + offq), idesc_s, kk > 0);
-            }
-#pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-              const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
-              const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
-              umma_ss(dpt_tm[w], umma_desc(kmaj, va + offk), umma_desc(kmaj, da + offq), idesc_s, kk > 0);
-            }
-            umma_commit(&sm.sdp_full[w]);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+            const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+            umma_ss_w(st_tm[w], umma_desc_add(k_desc, offk), umma_desc_add(qk, offq), idesc_s, kk > 0);
           }
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+            const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+            umma_ss_w(dpt_tm[w], umma_desc_add(v_desc, offk), umma_desc_add(dok, offq), idesc_s, kk > 0);
+          }
+          umma_commit_w(&sm.sdp_full[w]);
           state[w] = 1;
         } else {
           if (!warp_test(&sm.pds_ready[w], cnt[w] & 1, lane)) continue;
-          if (lane == 0) {
-            if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 910);
-            tc_fence_after();
+          if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 910);
+          tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < 64 / 16; ++kk) {
-              umma_ts(dv_tm, st_tm[w] + kk * 8, umma_desc(mnmaj64, da + kk * 2048), idesc_acc,
+          for (int kk = 0; kk < 64 / 16; ++kk) {
+            umma_ts_w(dv_tm, st_tm[w] + kk * 8, umma_desc_add(domn, kk * 2048), idesc_acc,
                       (acc_started || kk > 0) ? 1u : 0u);
-            }
-#pragma unroll
-            for (int kk = 0; kk < 64 / 16; ++kk) {
-              umma_ts(dk_tm, dpt_tm[w] + kk * 8, umma_desc(mnmaj64, qa + kk * 2048), idesc_acc,
-                      (acc_started || kk > 0) ? 1u : 0u);
-            }
-            umma_commit(&sm.qd_empty[st]);
           }
+#pragma unroll
+          for (int kk = 0; kk < 64 / 16; ++kk) {
+            umma_ts_w(dk_tm, dpt_tm[w] + kk * 8, umma_desc_add(qmn, kk * 2048), idesc_acc,
+                      (acc_started || kk > 0) ? 1u : 0u);
+          }
+          umma_commit_w(&sm.qd_empty[st]);
           acc_started = true;
           cnt[w]++;
           ntiles++;
@@ -714,13 +706,10 @@ __device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, 
         }
       }
     }
-    if (lane == 0) {
-      if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 911);
-      umma_commit(&sm.acc_done);
-      umma_commit(&sm.kv_empty);
-    }
+    if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 911);
+    umma_commit_w(&sm.acc_done);
+    umma_commit_w(&sm.kv_empty);
     tile_base += ntiles;
-    __syncwarp();
   }
 }
 

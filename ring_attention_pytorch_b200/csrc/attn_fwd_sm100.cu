@@ -162,7 +162,7 @@ __device__ __forceinline__ void producer_role(FwdSmem<D>& sm, const AttnFwdParam
 // warp 1: MMA issuer (all 32 lanes scan tiles, lane 0 issues tcgen05.mma)
 // ------------------------------------------------------------------------------------------------
 template <int D, bool BF16>
-__device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p, uint32_t tmem) {
+__device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p, uint32_t tmem_in) {
   constexpr uint32_t idesc_qk = umma_idesc_bf16(BM, BN, 0, 0, BF16 ? 1 : 0);
   constexpr uint32_t idesc_pv = umma_idesc_bf16(BM, D, 0, 1, BF16 ? 1 : 0);
   // K-major operands (Q, K): 8-row groups 1024 B apart; the leading offset is unused with 128B swizzle.
@@ -170,102 +170,99 @@ __device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p,
   // MN-major operand (V as B of P V): 64-wide d sub-tiles SUB_BYTES apart, 8-row kv groups 1024 B apart.
   constexpr uint64_t vmaj_static = umma_smem_desc_hi_lo(SUB_BYTES, 1024, UMMA_LAYOUT_SW128);
 
+  // The whole warp runs this role in lock step with warp-uniform values; the *_w wrappers elect one lane for
+  // the actual tcgen05 instruction.  Descriptors are built once and advanced with constant adds.
   const int lane = lane_id();
+  const uint32_t tmem = warp_uniform(tmem_in);
   uint32_t n_kv = 0;
   uint32_t cnt_p[2] = {0, 0};
   uint32_t items_t[2] = {0, 0};
-  const uint32_t s_tm[2] = {tmem + 0, tmem + 128};
-  const uint32_t o_tm[2] = {tmem + 256, tmem + 256 + D};
+  const uint32_t s_tm0 = tmem, s_tm1 = tmem + 128;
+  const uint32_t o_tm0 = tmem + 256, o_tm1 = tmem + 256 + D;
+  const uint64_t q_desc0 = umma_desc(kmaj_static, smem_u32(sm.q[0]));
+  const uint64_t q_desc1 = umma_desc(kmaj_static, smem_u32(sm.q[1]));
+  const uint64_t kv_kdesc0 = umma_desc(kmaj_static, smem_u32(sm.kv[0]));
+  const uint64_t kv_vdesc0 = umma_desc(vmaj_static, smem_u32(sm.kv[0]));
+  constexpr uint32_t SLOT16 = FwdSmem<D>::TILE_BYTES >> 4;
 
-  auto issue_qk = [&](int t, uint32_t kslot) {  // lane 0 only
-    const uint32_t qa = smem_u32(sm.q[t]);
-    const uint32_t ka = smem_u32(sm.kv[kslot]);
+  auto issue_qk = [&](const int t, const uint32_t kslot) {
+    const uint64_t kd = kv_kdesc0 + uint64_t(kslot * SLOT16);
+    const uint64_t qd = t ? q_desc1 : q_desc0;
+    const uint32_t st = t ? s_tm1 : s_tm0;
 #pragma unroll
     for (int kk = 0; kk < D / 16; ++kk) {
       const uint32_t off = (kk / 4) * SUB_BYTES + (kk % 4) * 32;
-      umma_ss(s_tm[t], umma_desc(kmaj_static, qa + off), umma_desc(kmaj_static, ka + off), idesc_qk, kk > 0);
+      umma_ss_w(st, umma_desc_add(qd, off), umma_desc_add(kd, off), idesc_qk, kk > 0);
     }
-    umma_commit(&sm.s_full[t]);
+    umma_commit_w(&sm.s_full[0] + t);
   };
 
   const int total = num_items(p);
   for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
     Item it;
     decode_item(p, idx, it);
-    if (lane == 0) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
-        if (it.tvalid[t]) mbar_wait(&sm.q_full[t], items_t[t] & 1, 200 + t);
-      tc_fence_after();
-    }
+    for (int t = 0; t < 2; ++t)
+      if (it.tvalid[t]) mbar_wait(&sm.q_full[t], items_t[t] & 1, 200 + t);
+    tc_fence_after();
 
     FwdScan scan;
     init_scan(scan, p, it);
     ScanTile cur, nxt;
     bool has = scan.next(lane, cur);
     bool pv_started[2] = {false, false};
-    if (has && lane == 0) {
+    if (has) {
       const uint32_t ks = (2 * n_kv) % NSLOT, kph = ((2 * n_kv) / NSLOT) & 1;
       mbar_wait(&sm.kv_full[ks], kph, 210);
       tc_fence_after();
 #pragma unroll
       for (int t = 0; t < 2; ++t)
         if (cur.need[t]) issue_qk(t, ks);
-      umma_commit(&sm.kv_empty[ks]);
+      umma_commit_w(&sm.kv_empty[ks]);
     }
     while (has) {
       const bool hasn = scan.next(lane, nxt);
-      if (lane == 0) {
-        const uint32_t vs = (2 * n_kv + 1) % NSLOT, vph = ((2 * n_kv + 1) / NSLOT) & 1;
-        const uint32_t ksn = (2 * n_kv + 2) % NSLOT, kphn = ((2 * n_kv + 2) / NSLOT) & 1;
-        mbar_wait(&sm.kv_full[vs], vph, 220);
-        tc_fence_after();
-        bool kwaited = false;
-        const uint32_t va = smem_u32(sm.kv[vs]);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (cur.need[t]) {
-            if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 230 + t);
-            mbar_wait(&sm.p_ready[t], cnt_p[t] & 1, 240 + t);
-            tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < BN / 16; ++kk) {
-              umma_ts(o_tm[t], s_tm[t] + kk * 8, umma_desc(vmaj_static, va + kk * 2048), idesc_pv,
-                      (pv_started[t] || kk > 0) ? 1u : 0u);
-            }
-            umma_commit(&sm.o_done[t]);
-          }
-          if (hasn && nxt.need[t]) {
-            if (!kwaited) {
-              mbar_wait(&sm.kv_full[ksn], kphn, 250);
-              tc_fence_after();
-              kwaited = true;
-            }
-            issue_qk(t, ksn);
-          }
-        }
-        umma_commit(&sm.kv_empty[vs]);
-        if (hasn) umma_commit(&sm.kv_empty[ksn]);
-      }
+      const uint32_t vs = (2 * n_kv + 1) % NSLOT, vph = ((2 * n_kv + 1) / NSLOT) & 1;
+      const uint32_t ksn = (2 * n_kv + 2) % NSLOT, kphn = ((2 * n_kv + 2) / NSLOT) & 1;
+      mbar_wait(&sm.kv_full[vs], vph, 220);
+      tc_fence_after();
+      bool kwaited = false;
+      const uint64_t vd = kv_vdesc0 + uint64_t(vs * SLOT16);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (cur.need[t]) {
+          if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 230 + t);
+          mbar_wait(&sm.p_ready[t], cnt_p[t] & 1, 240 + t);
+          tc_fence_after();
+          const uint32_t ot = t ? o_tm1 : o_tm0, st = t ? s_tm1 : s_tm0;
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            umma_ts_w(ot, st + kk * 8, umma_desc_add(vd, kk * 2048), idesc_pv, (pv_started[t] || kk > 0) ? 1u : 0u);
+          }
+          umma_commit_w(&sm.o_done[t]);
           pv_started[t] = true;
           cnt_p[t]++;
         }
+        if (hasn && nxt.need[t]) {
+          if (!kwaited) {
+            mbar_wait(&sm.kv_full[ksn], kphn, 250);
+            tc_fence_after();
+            kwaited = true;
+          }
+          issue_qk(t, ksn);
+        }
       }
+      umma_commit_w(&sm.kv_empty[vs]);
+      if (hasn) umma_commit_w(&sm.kv_empty[ksn]);
       n_kv++;
       cur = nxt;
       has = hasn;
-      __syncwarp();
     }
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       if (!it.tvalid[t]) continue;
-      if (lane == 0) {
-        if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 260 + t);
-        umma_commit(&sm.q_empty[t]);
-      }
+      if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 260 + t);
+      umma_commit_w(&sm.q_empty[t]);
       items_t[t]++;
     }
   }

@@ -220,6 +220,45 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-collective variants: every lane of the (converged) warp executes the statement with warp-uniform
+// operands and ONE elected lane issues.  Keeping the call site uniform lets ptxas hold descriptors in uniform
+// registers instead of emitting a per-MMA divergence-safe broadcast loop (profiles/ncu_r1b).
+__device__ __forceinline__ void umma_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+// Tell the compiler a value is warp-uniform (it came from shared memory, so ptxas cannot prove it).
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // All previously issued tcgen05.mma of this thread arrive on `bar` when complete
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -285,6 +324,11 @@ __host__ __device__ constexpr uint64_t umma_smem_desc_hi_lo(uint32_t lbo_bytes, 
 }
 __device__ __forceinline__ uint64_t umma_desc(uint64_t static_bits, uint32_t smem_addr) {
   return static_bits | uint64_t((smem_addr >> 4) & 0x3FFF);
+}
+// Advance a descriptor's start address by a byte offset (multiple of 16).  Shared-memory addresses are below
+// 256 KB, so the 14-bit (addr >> 4) field never carries into the neighbouring fields.
+__device__ __forceinline__ uint64_t umma_desc_add(uint64_t desc, uint32_t byte_off) {
+  return desc + uint64_t(byte_off >> 4);
 }
 constexpr uint32_t UMMA_LAYOUT_SW128 = 2;
 
