@@ -241,35 +241,44 @@ __device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, ui
         if (state[w] == 0) {
           if (!warp_test(&sm.k_full[ks], kph, lane)) continue;
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
-            umma_ss_w(x_tm[w], umma_desc_add(q_desc, off), umma_desc_add(kd, off), idesc_s, kk > 0);
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
+              umma_ss(x_tm[w], umma_desc_add(q_desc, off), umma_desc_add(kd, off), idesc_s, kk > 0);
+            }
+            umma_commit(&sm.s_full[w]);
           }
-          umma_commit_w(&sm.s_full[w]);
+          __syncwarp();
           state[w] = 1;
         } else if (state[w] == 1) {
           if (!warp_test(&sm.v_full[vs], vph, lane)) continue;
           if (!warp_test(&sm.s_taken[w], cnt[w] & 1, lane)) continue;
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
-            umma_ss_w(x_tm[w], umma_desc_add(do_desc, off), umma_desc_add(vd, off), idesc_s, kk > 0);
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
+              umma_ss(x_tm[w], umma_desc_add(do_desc, off), umma_desc_add(vd, off), idesc_s, kk > 0);
+            }
+            umma_commit(&sm.dp_full[w]);
+            umma_commit(&sm.v_empty[vs]);
           }
-          umma_commit_w(&sm.dp_full[w]);
-          umma_commit_w(&sm.v_empty[vs]);
+          __syncwarp();
           state[w] = 2;
         } else {
           if (!warp_test(&sm.ds_ready[w], cnt[w] & 1, lane)) continue;
           if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 610);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 128 / 16; ++kk) {
-            umma_ts_w(dq_tm, x_tm[w] + kk * 8, umma_desc_add(kmn, kk * 2048), idesc_dq,
+            for (int kk = 0; kk < 128 / 16; ++kk) {
+              umma_ts(dq_tm, x_tm[w] + kk * 8, umma_desc_add(kmn, kk * 2048), idesc_dq,
                       (dq_started || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&sm.k_empty[ks]);
           }
-          umma_commit_w(&sm.k_empty[ks]);
+          __syncwarp();
           dq_started = true;
           cnt[w]++;
           ntiles++;
@@ -286,7 +295,7 @@ __device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, ui
 
 template <int D, bool BF16>
 __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem) {
-  const int wg_tid = threadIdx.x - (128 + 128 * W);
+  const int wg_tid = threadIdx.x - 128 * W;
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
   const uint32_t x_tm = tmem + W * 128 + lane_off;
   const uint32_t dq_tm = tmem + 256 + lane_off;
@@ -488,7 +497,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_cons
     mbar_init(&sm.epi_done, 256);
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 10) {
     tmem_alloc(&sm.tmem_base, 512);
     tmem_relinquish();
   }
@@ -496,17 +505,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  if (warp < 4) {
+  if (warp >= 8) {  // control warps on the highest warp ids: the scheduler favours them
     setmaxnreg_dec<72>();
-    if (warp == 0) dq_producer<D>(sm, p, &map_qd, &map_kv);
-    if (warp == 1) dq_mma<D, BF16>(sm, p, tmem);
+    if (warp == 8) dq_producer<D>(sm, p, &map_qd, &map_kv);
+    if (warp == 9) dq_mma<D, BF16>(sm, p, tmem);
   } else {
     setmaxnreg_inc<216>();
-    dq_softmax<D, BF16>(sm, p, warp < 8 ? 0 : 1, tmem);
+    dq_softmax<D, BF16>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 10) tmem_dealloc(tmem, 512);
 }
 
 // =================================================================================================
@@ -670,35 +679,41 @@ __device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, 
         if (state[w] == 0) {
           if (!warp_test(&sm.qd_full[st], ph, lane)) continue;
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
-            const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
-            umma_ss_w(st_tm[w], umma_desc_add(k_desc, offk), umma_desc_add(qk, offq), idesc_s, kk > 0);
-          }
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+              const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+              umma_ss(st_tm[w], umma_desc_add(k_desc, offk), umma_desc_add(qk, offq), idesc_s, kk > 0);
+            }
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
-            const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
-            umma_ss_w(dpt_tm[w], umma_desc_add(v_desc, offk), umma_desc_add(dok, offq), idesc_s, kk > 0);
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+              const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+              umma_ss(dpt_tm[w], umma_desc_add(v_desc, offk), umma_desc_add(dok, offq), idesc_s, kk > 0);
+            }
+            umma_commit(&sm.sdp_full[w]);
           }
-          umma_commit_w(&sm.sdp_full[w]);
+          __syncwarp();
           state[w] = 1;
         } else {
           if (!warp_test(&sm.pds_ready[w], cnt[w] & 1, lane)) continue;
           if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 910);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 64 / 16; ++kk) {
-            umma_ts_w(dv_tm, st_tm[w] + kk * 8, umma_desc_add(domn, kk * 2048), idesc_acc,
+            for (int kk = 0; kk < 64 / 16; ++kk) {
+              umma_ts(dv_tm, st_tm[w] + kk * 8, umma_desc_add(domn, kk * 2048), idesc_acc,
                       (acc_started || kk > 0) ? 1u : 0u);
-          }
+            }
 #pragma unroll
-          for (int kk = 0; kk < 64 / 16; ++kk) {
-            umma_ts_w(dk_tm, dpt_tm[w] + kk * 8, umma_desc_add(qmn, kk * 2048), idesc_acc,
+            for (int kk = 0; kk < 64 / 16; ++kk) {
+              umma_ts(dk_tm, dpt_tm[w] + kk * 8, umma_desc_add(qmn, kk * 2048), idesc_acc,
                       (acc_started || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&sm.qd_empty[st]);
           }
-          umma_commit_w(&sm.qd_empty[st]);
+          __syncwarp();
           acc_started = true;
           cnt[w]++;
           ntiles++;
@@ -715,7 +730,7 @@ __device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, 
 
 template <int D, bool BF16>
 __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem) {
-  const int wg_tid = threadIdx.x - (128 + 128 * W);
+  const int wg_tid = threadIdx.x - 128 * W;
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
   const uint32_t st_tm = tmem + W * 128 + lane_off;
   const uint32_t dpt_tm = tmem + W * 128 + 64 + lane_off;
@@ -903,7 +918,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
     mbar_init(&sm.epi_done, 256);
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 10) {
     tmem_alloc(&sm.tmem_base, 512);
     tmem_relinquish();
   }
@@ -911,17 +926,17 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  if (warp < 4) {
+  if (warp >= 8) {  // control warps on the highest warp ids: the scheduler favours them
     setmaxnreg_dec<72>();
-    if (warp == 0) dkv_producer<D>(sm, p, &map_qd64, &map_kv);
-    if (warp == 1) dkv_mma<D, BF16>(sm, p, tmem);
+    if (warp == 8) dkv_producer<D>(sm, p, &map_qd64, &map_kv);
+    if (warp == 9) dkv_mma<D, BF16>(sm, p, tmem);
   } else {
     setmaxnreg_inc<216>();
-    dkv_softmax<D, BF16>(sm, p, warp < 8 ? 0 : 1, tmem);
+    dkv_softmax<D, BF16>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 10) tmem_dealloc(tmem, 512);
 }
 
 // =================================================================================================

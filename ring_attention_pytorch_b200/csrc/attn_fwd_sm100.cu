@@ -189,12 +189,15 @@ __device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p,
     const uint64_t kd = kv_kdesc0 + uint64_t(kslot * SLOT16);
     const uint64_t qd = t ? q_desc1 : q_desc0;
     const uint32_t st = t ? s_tm1 : s_tm0;
+    if (elect_one()) {  // one election per batch: 8 back-to-back UTCHMMA with 1-3 instructions in between
 #pragma unroll
-    for (int kk = 0; kk < D / 16; ++kk) {
-      const uint32_t off = (kk / 4) * SUB_BYTES + (kk % 4) * 32;
-      umma_ss_w(st, umma_desc_add(qd, off), umma_desc_add(kd, off), idesc_qk, kk > 0);
+      for (int kk = 0; kk < D / 16; ++kk) {
+        const uint32_t off = (kk / 4) * SUB_BYTES + (kk % 4) * 32;
+        umma_ss(st, umma_desc_add(qd, off), umma_desc_add(kd, off), idesc_qk, kk > 0);
+      }
+      umma_commit(&sm.s_full[0] + t);
     }
-    umma_commit_w(&sm.s_full[0] + t);
+    __syncwarp();
   };
 
   const int total = num_items(p);
@@ -235,11 +238,14 @@ __device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p,
           mbar_wait(&sm.p_ready[t], cnt_p[t] & 1, 240 + t);
           tc_fence_after();
           const uint32_t ot = t ? o_tm1 : o_tm0, st = t ? s_tm1 : s_tm0;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < BN / 16; ++kk) {
-            umma_ts_w(ot, st + kk * 8, umma_desc_add(vd, kk * 2048), idesc_pv, (pv_started[t] || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < BN / 16; ++kk) {
+              umma_ts(ot, st + kk * 8, umma_desc_add(vd, kk * 2048), idesc_pv, (pv_started[t] || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&sm.o_done[t]);
           }
-          umma_commit_w(&sm.o_done[t]);
+          __syncwarp();
           pv_started[t] = true;
           cnt_p[t]++;
         }
@@ -344,7 +350,7 @@ __device__ __forceinline__ uint32_t scale_packed(uint32_t w, float f) {
 
 template <int D, bool BF16>
 __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams& p, const int t, uint32_t tmem) {
-  const int wg_tid = threadIdx.x - (128 + 128 * t);
+  const int wg_tid = threadIdx.x - 128 * t;
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
   const uint32_t s_tm = tmem + t * 128 + lane_off;
   const uint32_t o_tm = tmem + 256 + t * D + lane_off;
@@ -555,11 +561,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     fence_mbar_init();
   }
-  if (warp == 0 && lane_id() == 0) {
+  // warps 0-7: softmax warpgroups (TMEM lane quadrant = warp % 4); warps 8-11: producer, MMA issuer, fetcher.
+  // The warp scheduler favours higher warp ids, so the latency-critical issuing warps sit on top.
+  if (warp == 8 && lane_id() == 0) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_kv);
   }
-  if (warp == 2) {
+  if (warp == 10) {
     tmem_alloc(&sm.tmem_base, 512);
     tmem_relinquish();
   }
@@ -568,23 +576,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp < 4) {
+  if (warp >= 8) {
     setmaxnreg_dec<72>();
-    if (warp == 0) {
+    if (warp == 8) {
       producer_role<D>(sm, p, &map_q, &map_kv);
-    } else if (warp == 1) {
+    } else if (warp == 9) {
       mma_role<D, BF16>(sm, p, tmem);
-    } else if (warp == 2) {
+    } else if (warp == 10) {
       if (lane_id() == 0) fetch_role<D>(sm, p);
     }
   } else {
     setmaxnreg_inc<216>();
-    softmax_role<D, BF16>(sm, p, warp < 8 ? 0 : 1, tmem);
+    softmax_role<D, BF16>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 10) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
