@@ -308,3 +308,52 @@ def test_ring_transformer_multi_gpu(striped):
     from dist_utils import run_distributed
 
     run_distributed(_module_worker_gpu, 2, striped, backend="nccl")
+
+
+def _ring_set_worker(rank, world, ring_size):
+    """world = ring_sets x ring_size: every ring set runs its own independent striped causal ring."""
+    import torch.distributed as dist
+
+    from ring_attention_pytorch_b200.ops.oracle import attention_with_positions
+    from ring_attention_pytorch_b200.ops.ring_cuda import ring_flash_attn_cuda
+    from ring_attention_pytorch_b200.parallel.layout import make_position_map
+
+    torch.manual_seed(0)
+    b, n, h, hk, d = 1, 384, 4, 2, 128
+    dev = torch.device("cuda", rank)
+    qs = [torch.randn(b, n, h, d, device=dev, dtype=torch.bfloat16) for _ in range(world)]
+    ks = [torch.randn(b, n, hk, d, device=dev, dtype=torch.bfloat16) for _ in range(world)]
+    vs = [torch.randn(b, n, hk, d, device=dev, dtype=torch.bfloat16) for _ in range(world)]
+    gs = [torch.randn(b, n, h, d, device=dev, dtype=torch.bfloat16) for _ in range(world)]
+    q, k, v = (t[rank].clone().requires_grad_() for t in (qs, ks, vs))
+    out = ring_flash_attn_cuda(q, k, v, None, True, 1024, True, True, None, ring_size)
+    dq, dk, dv = torch.autograd.grad(out, (q, k, v), gs[rank])
+    torch.cuda.synchronize()
+
+    ring_set = rank // ring_size
+    members = list(range(ring_set * ring_size, (ring_set + 1) * ring_size))
+    pm = make_position_map("striped", ring_size, n)
+    qf = {r: qs[r].float().requires_grad_() for r in members}
+    kf = {r: ks[r].float().requires_grad_() for r in members}
+    vf = {r: vs[r].float().requires_grad_() for r in members}
+    k_all = torch.cat([kf[r] for r in members], 1)
+    v_all = torch.cat([vf[r] for r in members], 1)
+    k_pos = torch.cat([pm.positions(i, dev) for i in range(ring_size)])
+    loss, outs = 0, {}
+    for i, r in enumerate(members):
+        o = attention_with_positions(qf[r], k_all, v_all, pm.positions(i, dev), k_pos, causal=True)
+        outs[r] = o
+        loss = loss + (o * gs[r].float()).sum()
+    loss.backward()
+    assert (out.float() - outs[rank]).abs().max() < 3e-2
+    for got, ref in ((dq, qf[rank].grad), (dk, kf[rank].grad), (dv, vf[rank].grad)):
+        assert (got.float() - ref).abs().max() / ref.abs().max() < 3e-2
+    dist.barrier()
+
+
+def test_ring_sets_four_gpus():
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs >= 4 GPUs")
+    from dist_utils import run_distributed
+
+    run_distributed(_ring_set_worker, 4, 2, backend="nccl")
