@@ -287,7 +287,7 @@ std::tuple<Tensor, Tensor> attn_bwd_dkdv(const Tensor& qdo_buf, const Tensor& kv
 // ---------------------------------------------------------------------------------------------
 void tree_decode_partial(const Tensor& q, const c10::optional<Tensor>& k, const c10::optional<Tensor>& v,
                          const c10::optional<Tensor>& k_scale, const c10::optional<Tensor>& v_scale, Tensor scratch,
-                         Tensor partial, int64_t kv_heads, int64_t splits, double scale) {
+                         Tensor partial, int64_t kv_heads, int64_t splits, double scale, int64_t scale_block_keys) {
   TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kFloat && q.is_contiguous() && q.dim() == 3);
   const int b = q.size(0), h = q.size(1), d = q.size(2);
   TORCH_CHECK(d == 64 || d == 128, "tree decode supports head dim 64 or 128");
@@ -310,20 +310,28 @@ void tree_decode_partial(const Tensor& q, const c10::optional<Tensor>& k, const 
   }
   const float* ksp = nullptr;
   const float* vsp = nullptr;
+  int n_scale_blocks = 1;
   if (k_scale.has_value()) {
-    TORCH_CHECK(k_scale->scalar_type() == at::kFloat && k_scale->numel() == b * kv_heads && k_scale->is_contiguous());
+    TORCH_CHECK(v_scale.has_value() && k_scale->sizes() == v_scale->sizes(), "k_scale and v_scale come together");
+    TORCH_CHECK(k_scale->scalar_type() == at::kFloat && v_scale->scalar_type() == at::kFloat);
+    TORCH_CHECK(k_scale->is_contiguous() && v_scale->is_contiguous() && k_scale->numel() % (b * kv_heads) == 0);
+    n_scale_blocks = k_scale->numel() / (b * kv_heads);
     ksp = k_scale->data_ptr<float>();
-  }
-  if (v_scale.has_value()) {
-    TORCH_CHECK(v_scale->scalar_type() == at::kFloat && v_scale->numel() == b * kv_heads && v_scale->is_contiguous());
     vsp = v_scale->data_ptr<float>();
+  }
+  // keys per scale block: the whole shard for per-head scales, otherwise ceil(n / blocks) rounded to the 64-key tile
+  int scale_block = 1 << 30;
+  if (n_scale_blocks > 1) {
+    TORCH_CHECK(scale_block_keys > 0 && scale_block_keys % 64 == 0, "scale_block_keys must be a multiple of 64");
+    TORCH_CHECK((int64_t)n_scale_blocks * scale_block_keys >= n, "not enough scale blocks for the shard");
+    scale_block = (int)scale_block_keys;
   }
   TORCH_CHECK(scratch.scalar_type() == at::kFloat && scratch.is_contiguous() &&
               scratch.numel() >= (int64_t)b * kv_heads * splits * (h / kv_heads) * (d + 2));
   c10::cuda::CUDAGuard guard(q.device());
   rab::launch_tree_decode_partial(q.data_ptr<float>(), kp, vp, ksp, vsp, scratch.data_ptr<float>(),
                                   partial.data_ptr<float>(), b, h, (int)kv_heads, n, d, (int)splits, kind,
-                                  (float)scale, at::cuda::getCurrentCUDAStream());
+                                  (float)scale, scale_block, n_scale_blocks, at::cuda::getCurrentCUDAStream());
 }
 
 void tree_decode_reduce(at::IntArrayRef partial_ptrs, Tensor out, double eps) {
@@ -407,7 +415,7 @@ TORCH_LIBRARY(rab, m) {
         "base1, int q_pos_offset, int[] hop_owner) -> (Tensor, Tensor)");
   m.def("pack_kv(Tensor k, Tensor v, Tensor(a!) slot) -> ()");
   m.def("tree_decode_partial(Tensor q, Tensor? k, Tensor? v, Tensor? k_scale, Tensor? v_scale, Tensor(a!) scratch, "
-        "Tensor(b!) partial, int kv_heads, int splits, float scale) -> ()");
+        "Tensor(b!) partial, int kv_heads, int splits, float scale, int scale_block_keys) -> ()");
   m.def("tree_decode_reduce(int[] partial_ptrs, Tensor(a!) out, float eps) -> ()");
   m.def("bwd_prep(Tensor q, Tensor o, Tensor dout, Tensor lse, Tensor(a!) qdo_buf, Tensor(b!) stat_buf, int rank) -> ()");
   m.def("attn_bwd_dq(Tensor qdo_buf, Tensor kv_buf, Tensor stat_buf, Tensor? ready, int ready_target, Tensor? "

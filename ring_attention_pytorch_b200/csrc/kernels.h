@@ -122,12 +122,13 @@ void launch_bwd_prep(const void* q, const void* o, const void* dout, const float
 // ------------------------------------------------------------------------------------------------
 // tree-attention decode (tree_decode_sm100.cu)
 // ------------------------------------------------------------------------------------------------
-// q [b, h, d] fp32; k, v [b*hk, n, d] (kv_kind 0 bf16, 1 fp16, 2 fp8-e4m3 with per-(b*hk) scales or null)
+// q [b, h, d] fp32; k, v [b*hk, n, d] (kv_kind 0 bf16, 1 fp16, 2 fp8-e4m3); k_scale / v_scale: null or
+// [b*hk][n_scale_blocks] fp32 block scales, one per `scale_block` keys (scale_block % 64 == 0)
 // scratch [b*hk][splits][g][d+2] fp32; partial [b*h][d+2] fp32 = (out, lse*log2e, valid)
 void launch_tree_decode_partial(const float* q, const void* k, const void* v, const float* k_scale,
                                 const float* v_scale, float* scratch, float* partial, int batch, int heads,
-                                int kv_heads, int n, int d, int splits, int kv_kind, float scale,
-                                cudaStream_t stream);
+                                int kv_heads, int n, int d, int splits, int kv_kind, float scale, int scale_block,
+                                int n_scale_blocks, cudaStream_t stream);
 struct TreeReduceParams {
   int world;
   const float* partials[kMaxWorld];  // every rank's [b*h][d+2] partial (peer-mapped)

@@ -89,14 +89,14 @@ __global__ void __launch_bounds__(TD_THREADS)
 tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__ k, const void* __restrict__ v,
                            const float* __restrict__ k_scale, const float* __restrict__ v_scale,
                            float* __restrict__ scratch, int heads, int kv_heads, int n, int splits,
-                           float scale_log2) {
+                           float scale_log2, int scale_block, int n_scale_blocks) {
   const int g_total = heads / kv_heads;
   const int g0 = blockIdx.z * TD_MAX_G;                 // first group member handled by this CTA
   const int g = min(TD_MAX_G, g_total - g0);
   const int bhk = blockIdx.y;
   const int b = bhk / kv_heads, kvh = bhk % kv_heads;
   const int split = blockIdx.x;
-  const int per = (n + splits - 1) / splits;
+  const int per = ((n + splits - 1) / splits + TD_TILE - 1) / TD_TILE * TD_TILE;  // tile-aligned splits
   const int k0 = split * per, k1 = min(n, k0 + per);
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
@@ -104,8 +104,10 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
   __shared__ float corr_s[TD_MAX_G];
   __shared__ float red_s[8][TD_MAX_G][D + 1];
 
-  const float ks = k_scale ? k_scale[bhk] : 1.f;
-  const float vs = v_scale ? v_scale[bhk] : 1.f;
+  // Block-scaled KV (fp8 serve path): one fp32 scale per `scale_block` keys of every (batch, kv head), applied to
+  // the scores (K) and folded into the probabilities (V).  scale_block is a multiple of the 64-key tile.
+  const float* ksb = k_scale ? k_scale + (size_t)bhk * n_scale_blocks : nullptr;
+  const float* vsb = v_scale ? v_scale + (size_t)bhk * n_scale_blocks : nullptr;
 
   // QK ownership: 8 lanes per key (each lane D/8 elements), 4 keys per warp step, 16 keys per warp per tile
   constexpr int EPL = D / 8;  // elements per lane: 16 (D=128) or 8 (D=64)
@@ -116,8 +118,7 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
       // query head j uses kv head j % kv_heads  ->  heads {kvh, kvh + hk, ...}
-      qr[gi][e] = gi < g ? q[((size_t)b * heads + (g0 + gi) * kv_heads + kvh) * D + l8 * EPL + e] * scale_log2 * ks
-                         : 0.f;
+      qr[gi][e] = gi < g ? q[((size_t)b * heads + (g0 + gi) * kv_heads + kvh) * D + l8 * EPL + e] * scale_log2 : 0.f;
     }
   }
 
@@ -138,6 +139,8 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
   const uint8_t* vbase = reinterpret_cast<const uint8_t*>(v) + (size_t)bhk * n * D * eb;
 
   for (int t0 = k0; t0 < k1; t0 += TD_TILE) {
+    const float ks = ksb ? ksb[t0 / scale_block] : 1.f;
+    const float vs = vsb ? vsb[t0 / scale_block] : 1.f;
     // ---- scores -------------------------------------------------------------------------------
     float kf[4][EPL];
 #pragma unroll
@@ -160,7 +163,7 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
         a += __shfl_xor_sync(0xffffffffu, a, 1);
         a += __shfl_xor_sync(0xffffffffu, a, 2);
         a += __shfl_xor_sync(0xffffffffu, a, 4);
-        part[gi] = live ? a : -INFINITY;
+        part[gi] = live ? a * ks : -INFINITY;
       }
       if (l8 == 0) *reinterpret_cast<float4*>(&s_s[kl][0]) = make_float4(part[0], part[1], part[2], part[3]);
     }
@@ -180,8 +183,8 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       const float corr = m_prev == -INFINITY ? 0.f : fast_exp2(m_prev - m_eff);
-      s_s[lane][gi] = pa;
-      s_s[lane + 32][gi] = pb;
+      s_s[lane][gi] = pa * vs;  // V block scale rides on the probabilities (the denominator uses the unscaled p)
+      s_s[lane + 32][gi] = pb * vs;
       m_run = m_new;
       l_run = l_prev * corr + sum;
       if (lane == 0) corr_s[gi] = corr;
@@ -242,7 +245,7 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
     float sacc = 0.f;
 #pragma unroll
     for (int kg = 0; kg < 8; ++kg) sacc += red_s[kg][gi][c];
-    out[gi * (D + 2) + c] = sacc * vs;
+    out[gi * (D + 2) + c] = sacc;
   }
   if (warp < g && lane == 0) {
     out[warp * (D + 2) + D] = m_run;
@@ -321,14 +324,14 @@ __global__ void tree_decode_reduce_kernel(const __grid_constant__ TreeReducePara
 
 void launch_tree_decode_partial(const float* q, const void* k, const void* v, const float* k_scale,
                                 const float* v_scale, float* scratch, float* partial, int batch, int heads,
-                                int kv_heads, int n, int d, int splits, int kv_kind, float scale,
-                                cudaStream_t stream) {
+                                int kv_heads, int n, int d, int splits, int kv_kind, float scale, int scale_block,
+                                int n_scale_blocks, cudaStream_t stream) {
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(splits, batch * kv_heads, (heads / kv_heads + TD_MAX_G - 1) / TD_MAX_G);
   if (n > 0) {
 #define RAB_TD_LAUNCH(DD, KK)                                                                                   \
-  tree_decode_partial_kernel<DD, KK><<<grid, TD_THREADS, 0, stream>>>(q, k, v, k_scale, v_scale, scratch, heads, \
-                                                                      kv_heads, n, splits, scale_log2)
+  tree_decode_partial_kernel<DD, KK><<<grid, TD_THREADS, 0, stream>>>(                                          \
+      q, k, v, k_scale, v_scale, scratch, heads, kv_heads, n, splits, scale_log2, scale_block, n_scale_blocks)
     if (d == 128) {
       if (kv_kind == 0) RAB_TD_LAUNCH(128, 0);
       else if (kv_kind == 1) RAB_TD_LAUNCH(128, 1);

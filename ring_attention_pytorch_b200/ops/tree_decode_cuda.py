@@ -29,10 +29,13 @@ def tree_decode_cuda(
     eps: float = 1e-8,
     k_scale: Optional[Tensor] = None,
     v_scale: Optional[Tensor] = None,
+    scale_block_keys: int = 0,
 ) -> Tensor:
     """q [b, h, 1, d]; k, v [b, hk, n, d] this rank's shard (bf16 / fp16 / float8_e4m3fn) or None.
 
-    ``k_scale`` / ``v_scale``: optional per-(batch, kv head) fp32 dequantisation scales for the fp8 path.
+    ``k_scale`` / ``v_scale``: optional fp32 dequantisation scales for the fp8 path, either per (batch, kv head)
+    (``numel == b*hk``) or block-scaled ``[b*hk, n_blocks]`` with one scale per ``scale_block_keys`` keys
+    (a multiple of 64).
     Returns [b, h, 1, d] in q's dtype (fp32 if q is fp32).
     """
     ops = _ext.ops()
@@ -63,13 +66,13 @@ def tree_decode_cuda(
         ws = get_workspace(get_world_size(), dev)
         stage, peer_ptrs = ws.staging("tree_partial", nbytes)
         partial = stage.view(torch.float32)
-        ops.tree_decode_partial(qf, k, v, k_scale, v_scale, scratch, partial, hk, splits, scale)
+        ops.tree_decode_partial(qf, k, v, k_scale, v_scale, scratch, partial, hk, splits, scale, scale_block_keys)
         ws.barrier()
         ops.tree_decode_reduce(peer_ptrs, out, eps)
         LAUNCHES["count"] += 4 if n > 0 else 3
     else:
         partial = torch.empty(b * h * (d + 2), dtype=torch.float32, device=dev)
-        ops.tree_decode_partial(qf, k, v, k_scale, v_scale, scratch, partial, hk, splits, scale)
+        ops.tree_decode_partial(qf, k, v, k_scale, v_scale, scratch, partial, hk, splits, scale, scale_block_keys)
         ops.tree_decode_reduce([partial.data_ptr()], out, eps)
         LAUNCHES["count"] += 3 if n > 0 else 2
     return out.view(b, h, 1, d)

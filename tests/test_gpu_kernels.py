@@ -357,3 +357,29 @@ def test_ring_sets_four_gpus():
     from dist_utils import run_distributed
 
     run_distributed(_ring_set_worker, 4, 2, backend="nccl")
+
+
+def test_tree_decode_block_scaled_fp8_kv():
+    """fp8-e4m3 KV cache with one fp32 scale per 128 keys of every (batch, kv head)."""
+    from ring_attention_pytorch_b200.ops.tree_decode_cuda import tree_decode_cuda
+
+    torch.manual_seed(0)
+    b, h, hk, n, d, blk = 2, 8, 2, 1000, 128, 128
+    q = torch.randn(b, h, 1, d, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(b, hk, n, d, device="cuda") * torch.linspace(0.5, 4.0, n, device="cuda")[None, None, :, None]
+    v = torch.randn(b, hk, n, d, device="cuda") * torch.linspace(3.0, 0.3, n, device="cuda")[None, None, :, None]
+    nb = (n + blk - 1) // blk
+    pad = nb * blk - n
+
+    def quant(t):
+        tp = torch.nn.functional.pad(t, (0, 0, 0, pad)).view(b, hk, nb, blk, d)
+        sc = tp.abs().amax(dim=(3, 4)).clamp(min=1e-6) / 448.0
+        q8 = (tp / sc[..., None, None]).to(torch.float8_e4m3fn)
+        deq = (q8.float() * sc[..., None, None]).view(b, hk, nb * blk, d)[:, :, :n]
+        return q8.view(b, hk, nb * blk, d)[:, :, :n].contiguous(), sc.reshape(b * hk, nb).contiguous(), deq
+
+    k8, ks, kd = quant(k)
+    v8, vs, vd = quant(v)
+    out = tree_decode_cuda(q, k8, v8, dim_v=d, k_scale=ks, v_scale=vs, scale_block_keys=blk)
+    ref = _dense_decode(q, kd, vd)
+    assert (out.float() - ref).abs().max() < 3e-2
