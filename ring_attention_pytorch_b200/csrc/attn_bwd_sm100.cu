@@ -364,14 +364,20 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
       // P = exp2(S*c - lse) while the tensor core is busy with dP = dO V^T of this tile (masked logits are
       // -inf and give exactly 0)
       if (!clamp) {
+        const float2 mul2 = make_float2(mul, mul), nl2 = make_float2(-lse2, -lse2);
 #pragma unroll
-        for (int j = 0; j < 128; ++j) sr[j] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(sr[j]), mul, -lse2)));
+        for (int j = 0; j < 128; j += 2) {
+          const float2 a = ffma2(make_float2(__uint_as_float(sr[j]), __uint_as_float(sr[j + 1])), mul2, nl2);
+          sr[j] = __float_as_uint(fast_exp2(a.x));
+          sr[j + 1] = __float_as_uint(fast_exp2(a.y));
+        }
       }
       mbar_wait((&sm.dp_full[0] + W), cnt & 1, 710 + W);
       tc_fence_after();
       // dS = P o (dP - delta) [* (1 - tanh^2) with softclamp]; the softmax scale is folded into the epilogue.
       if (!clamp) {
         uint32_t dpa[32], dpb[32];
+        const float2 nd2 = make_float2(-delta, -delta);
         tmem_ld32(x_tm, dpa);
 #pragma unroll
         for (int c = 0; c < 4; c += 2) {
@@ -381,9 +387,9 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
             uint32_t w16[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float d0 = __uint_as_float(sr[c * 32 + 2 * i]) * (__uint_as_float(dpa[2 * i]) - delta);
-              const float d1 = __uint_as_float(sr[c * 32 + 2 * i + 1]) * (__uint_as_float(dpa[2 * i + 1]) - delta);
-              w16[i] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
+              const float2 t = fadd2(make_float2(__uint_as_float(dpa[2 * i]), __uint_as_float(dpa[2 * i + 1])), nd2);
+              const float2 dd = fmul2(make_float2(__uint_as_float(sr[c * 32 + 2 * i]), __uint_as_float(sr[c * 32 + 2 * i + 1])), t);
+              w16[i] = BF16 ? pack_bf16x2(dd.x, dd.y) : pack_f16x2(dd.x, dd.y);
             }
             tc_wait_ld();  // chunk c+1 must have left TMEM before its columns are reused below
             if (c + 2 < 4) tmem_ld32(x_tm + (c + 2) * 32, dpa);
@@ -393,10 +399,10 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
             uint32_t w16[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float d0 = __uint_as_float(sr[(c + 1) * 32 + 2 * i]) * (__uint_as_float(dpb[2 * i]) - delta);
-              const float d1 =
-                  __uint_as_float(sr[(c + 1) * 32 + 2 * i + 1]) * (__uint_as_float(dpb[2 * i + 1]) - delta);
-              w16[i] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
+              const float2 t = fadd2(make_float2(__uint_as_float(dpb[2 * i]), __uint_as_float(dpb[2 * i + 1])), nd2);
+              const float2 dd = fmul2(
+                  make_float2(__uint_as_float(sr[(c + 1) * 32 + 2 * i]), __uint_as_float(sr[(c + 1) * 32 + 2 * i + 1])), t);
+              w16[i] = BF16 ? pack_bf16x2(dd.x, dd.y) : pack_f16x2(dd.x, dd.y);
             }
             tmem_st16(x_tm + (c + 1) * 16, w16);
           }
@@ -782,10 +788,12 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
 #pragma unroll
         for (int q4 = 0; q4 < 16; ++q4) {
           const float4 lv = l4[q4];
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 0]), mul, -lv.x));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 1]), mul, -lv.y));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 2]), mul, -lv.z));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(sr[q4 * 4 + 3]), mul, -lv.w));
+          const float2 mul2 = make_float2(mul, mul);
+          const float2 a01 = ffma2(make_float2(__uint_as_float(sr[q4 * 4 + 0]), __uint_as_float(sr[q4 * 4 + 1])), mul2,
+                                   make_float2(-lv.x, -lv.y));
+          const float2 a23 = ffma2(make_float2(__uint_as_float(sr[q4 * 4 + 2]), __uint_as_float(sr[q4 * 4 + 3])), mul2,
+                                   make_float2(-lv.z, -lv.w));
+          const float p0 = fast_exp2(a01.x), p1 = fast_exp2(a01.y), p2 = fast_exp2(a23.x), p3 = fast_exp2(a23.y);
           sr[q4 * 4 + 0] = __float_as_uint(p0);
           sr[q4 * 4 + 1] = __float_as_uint(p1);
           sr[q4 * 4 + 2] = __float_as_uint(p2);
@@ -797,12 +805,14 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
 #pragma unroll
         for (int q4 = 0; q4 < 16; ++q4) {
           const float4 dv = d4[q4];
-          const float e0 = __uint_as_float(sr[q4 * 4 + 0]) * (__uint_as_float(dp[q4 * 4 + 0]) - dv.x);
-          const float e1 = __uint_as_float(sr[q4 * 4 + 1]) * (__uint_as_float(dp[q4 * 4 + 1]) - dv.y);
-          const float e2 = __uint_as_float(sr[q4 * 4 + 2]) * (__uint_as_float(dp[q4 * 4 + 2]) - dv.z);
-          const float e3 = __uint_as_float(sr[q4 * 4 + 3]) * (__uint_as_float(dp[q4 * 4 + 3]) - dv.w);
-          dw[q4 * 2] = BF16 ? pack_bf16x2(e0, e1) : pack_f16x2(e0, e1);
-          dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(e2, e3) : pack_f16x2(e2, e3);
+          const float2 t01 = fadd2(make_float2(__uint_as_float(dp[q4 * 4 + 0]), __uint_as_float(dp[q4 * 4 + 1])),
+                                   make_float2(-dv.x, -dv.y));
+          const float2 t23 = fadd2(make_float2(__uint_as_float(dp[q4 * 4 + 2]), __uint_as_float(dp[q4 * 4 + 3])),
+                                   make_float2(-dv.z, -dv.w));
+          const float2 e01 = fmul2(make_float2(__uint_as_float(sr[q4 * 4 + 0]), __uint_as_float(sr[q4 * 4 + 1])), t01);
+          const float2 e23 = fmul2(make_float2(__uint_as_float(sr[q4 * 4 + 2]), __uint_as_float(sr[q4 * 4 + 3])), t23);
+          dw[q4 * 2] = BF16 ? pack_bf16x2(e01.x, e01.y) : pack_f16x2(e01.x, e01.y);
+          dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(e23.x, e23.y) : pack_f16x2(e23.x, e23.y);
         }
       } else {
         tc_wait_ld();  // dP^T has landed

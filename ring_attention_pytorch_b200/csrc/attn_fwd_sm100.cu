@@ -404,7 +404,7 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
         mb0 = w[0]; mb1 = w[1]; mb2 = w[2]; mb3 = w[3];
       }
 
-      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+      float2 ls01 = make_float2(0.f, 0.f), ls23 = make_float2(0.f, 0.f);
 
       // one 32-column chunk: mask, lazy max, exp2, pack, store P chunk
       auto process = [&](uint32_t (&x)[32], const int c) {
@@ -439,7 +439,8 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
           const float m_new = fmaxf(m_used, cmax);
           const float factor = (m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_new);
           l *= factor;
-          ls0 *= factor; ls1 *= factor; ls2 *= factor; ls3 *= factor;
+          ls01 = fmul2(ls01, make_float2(factor, factor));
+          ls23 = fmul2(ls23, make_float2(factor, factor));
           if (have_o) {
             // the previous P V of this tile completed before S became visible (commit ordering)
 #pragma unroll 1
@@ -464,16 +465,19 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
           m_used = m_new;
         }
         const float m_eff = (m_used == -INFINITY) ? 0.f : m_used;
+        const float2 mul2 = make_float2(mul, mul), negm2 = make_float2(-m_eff, -m_eff);
         uint32_t w16[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(x[2 * i]), mul, -m_eff));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(x[2 * i + 1]), mul, -m_eff));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(x[2 * i + 2]), mul, -m_eff));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(x[2 * i + 3]), mul, -m_eff));
-          ls0 += p0; ls1 += p1; ls2 += p2; ls3 += p3;
-          w16[i] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
-          w16[i + 1] = BF16 ? pack_bf16x2(p2, p3) : pack_f16x2(p2, p3);
+          // packed FFMA2 / FADD2: two logits per issue slot
+          const float2 a = ffma2(make_float2(__uint_as_float(x[2 * i]), __uint_as_float(x[2 * i + 1])), mul2, negm2);
+          const float2 bq = ffma2(make_float2(__uint_as_float(x[2 * i + 2]), __uint_as_float(x[2 * i + 3])), mul2, negm2);
+          const float2 pa = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+          const float2 pb = make_float2(fast_exp2(bq.x), fast_exp2(bq.y));
+          ls01 = fadd2(ls01, pa);
+          ls23 = fadd2(ls23, pb);
+          w16[i] = BF16 ? pack_bf16x2(pa.x, pa.y) : pack_f16x2(pa.x, pa.y);
+          w16[i + 1] = BF16 ? pack_bf16x2(pb.x, pb.y) : pack_f16x2(pb.x, pb.y);
         }
         tmem_st16(s_tm + c * 16, w16);
       };
@@ -489,7 +493,7 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
         if (c + 2 < 4) tmem_ld32(s_tm + (c + 2) * 32, xa);
         process(xb, c + 1);
       }
-      l += (ls0 + ls1) + (ls2 + ls3);
+      l += (ls01.x + ls01.y) + (ls23.x + ls23.y);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(p_ready);

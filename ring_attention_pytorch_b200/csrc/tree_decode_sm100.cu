@@ -112,13 +112,14 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
   // QK ownership: 8 lanes per key (each lane D/8 elements), 4 keys per warp step, 16 keys per warp per tile
   constexpr int EPL = D / 8;  // elements per lane: 16 (D=128) or 8 (D=64)
   const int sub = lane / 8, l8 = lane % 8;
-  float qr[TD_MAX_G][EPL];
+  float2 qr[TD_MAX_G][EPL / 2];  // packed pairs: the dot products run on FFMA2
 #pragma unroll
   for (int gi = 0; gi < TD_MAX_G; ++gi) {
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) {
+    for (int e = 0; e < EPL / 2; ++e) {
       // query head j uses kv head j % kv_heads  ->  heads {kvh, kvh + hk, ...}
-      qr[gi][e] = gi < g ? q[((size_t)b * heads + (g0 + gi) * kv_heads + kvh) * D + l8 * EPL + e] * scale_log2 : 0.f;
+      const float* qp = q + ((size_t)b * heads + (g0 + gi) * kv_heads + kvh) * D + l8 * EPL + 2 * e;
+      qr[gi][e] = gi < g ? make_float2(qp[0] * scale_log2, qp[1] * scale_log2) : make_float2(0.f, 0.f);
     }
   }
 
@@ -127,11 +128,11 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
   constexpr int KGROUPS = TD_THREADS / CHUNKS;  // 8 or 16
   constexpr int KPT = TD_TILE / KGROUPS;        // keys per thread per tile: 8 or 4
   const int chunk = tid % CHUNKS, kgrp = tid / CHUNKS;
-  float acc[TD_MAX_G][8];
+  float2 acc[TD_MAX_G][4];
 #pragma unroll
   for (int gi = 0; gi < TD_MAX_G; ++gi)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[gi][e] = 0.f;
+    for (int e = 0; e < 4; ++e) acc[gi][e] = make_float2(0.f, 0.f);
   float m_run = -INFINITY, l_run = 0.f;  // warp gi keeps the running stats of head gi (identical in all lanes)
 
   const size_t eb = kv_elem_bytes<KV_KIND>();
@@ -157,9 +158,11 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
       float part[TD_MAX_G];
 #pragma unroll
       for (int gi = 0; gi < TD_MAX_G; ++gi) {
-        float a = 0.f;
+        float2 a2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) a = fmaf(kf[step][e], qr[gi][e], a);
+        for (int e = 0; e < EPL / 2; ++e)
+          a2 = ffma2(make_float2(kf[step][2 * e], kf[step][2 * e + 1]), qr[gi][e], a2);
+        float a = a2.x + a2.y;
         a += __shfl_xor_sync(0xffffffffu, a, 1);
         a += __shfl_xor_sync(0xffffffffu, a, 2);
         a += __shfl_xor_sync(0xffffffffu, a, 4);
@@ -205,8 +208,9 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
 #pragma unroll
     for (int gi = 0; gi < TD_MAX_G; ++gi) {
       const float c = corr_s[gi];
+      const float2 c2 = make_float2(c, c);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[gi][e] *= c;
+      for (int e = 0; e < 4; ++e) acc[gi][e] = fmul2(acc[gi][e], c2);
     }
 #pragma unroll
     for (int i = 0; i < KPT; ++i) {
@@ -215,8 +219,10 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
       const float pk[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
       for (int gi = 0; gi < TD_MAX_G; ++gi) {
+        const float2 p2 = make_float2(pk[gi], pk[gi]);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[gi][e] = fmaf(pk[gi], vf[i][e], acc[gi][e]);
+        for (int e = 0; e < 4; ++e)
+          acc[gi][e] = ffma2(p2, make_float2(vf[i][2 * e], vf[i][2 * e + 1]), acc[gi][e]);
       }
     }
     __syncthreads();
@@ -227,7 +233,10 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
   for (int gi = 0; gi < g; ++gi) {
     if (kgrp < 8) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) red_s[kgrp][gi][chunk * 8 + e] = acc[gi][e];
+      for (int e = 0; e < 4; ++e) {
+        red_s[kgrp][gi][chunk * 8 + 2 * e] = acc[gi][e].x;
+        red_s[kgrp][gi][chunk * 8 + 2 * e + 1] = acc[gi][e].y;
+      }
     }
   }
   __syncthreads();
@@ -235,7 +244,10 @@ tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__
     for (int gi = 0; gi < g; ++gi) {
       if (kgrp >= 8) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(&red_s[kgrp - 8][gi][chunk * 8 + e], acc[gi][e]);
+        for (int e = 0; e < 4; ++e) {
+          atomicAdd(&red_s[kgrp - 8][gi][chunk * 8 + 2 * e], acc[gi][e].x);
+          atomicAdd(&red_s[kgrp - 8][gi][chunk * 8 + 2 * e + 1], acc[gi][e].y);
+        }
       }
     }
     __syncthreads();
