@@ -39,7 +39,8 @@ __global__ void device_barrier_kernel(const __grid_constant__ BarrierParams p) {
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(mine) - p.epoch) < 0) {
       __nanosleep(100);
-      if (clock64() - t0 > RAB_WATCHDOG_CYCLES) {
+      // ranks may reach their first barrier seconds apart (lazy module loading, allocator warm-up): be generous
+      if (clock64() - t0 > 8 * RAB_WATCHDOG_CYCLES) {
         printf("[rab] device barrier watchdog: rank %d waiting for %d epoch %u (have %u)\n", p.rank, peer, p.epoch,
                ld_acquire_sys(mine));
         __trap();

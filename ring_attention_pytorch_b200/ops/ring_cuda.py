@@ -39,6 +39,13 @@ from ring_attention_pytorch_b200.parallel.symm import get_workspace
 # counts launches of our own kernels (bench.py reports it as gpu_launches)
 LAUNCHES = {"count": 0}
 
+# save_kv_gather=True : the forward's gathered K/V ([W, 2, b*hk, n, d], i.e. the whole ring's K/V) is kept for the
+#                       backward, whose dQ kernel then needs no communication at all (fastest).
+# save_kv_gather=False: only this rank's K/V slot is kept (O(n) activation memory per layer, the classic ring
+#                       attention footprint); the backward re-pulls the peers' slots with the copy engines before
+#                       the dQ kernel starts.
+CONFIG = {"save_kv_gather": True}
+
 
 def _count(n: int = 1) -> None:
     LAUNCHES["count"] += n
@@ -131,9 +138,11 @@ class RingFlashAttentionCUDAFunction(Function):
                                 window=max_lookback_seq_len, scale=scale, softclamp=softclamp, q_pos_offset=q_off)
         _count()
 
+        keep_gather = CONFIG["save_kv_gather"] or not use_ring
         ctx.cfg = (causal, max_lookback_seq_len, ring_size, rank, layout, softclamp, scale, q_off, use_ring, d, d_pad,
-                   orig_dtype, hk)
-        ctx.save_for_backward(qp, o, lse, kv_gather, kbits if kbits is not None else torch.empty(0, device=dev))
+                   orig_dtype, hk, keep_gather)
+        kv_saved = kv_gather if keep_gather else kv_gather[rank].clone()
+        ctx.save_for_backward(qp, o, lse, kv_saved, kbits if kbits is not None else torch.empty(0, device=dev))
         out = o[..., :d]
         return out.to(orig_dtype) if orig_dtype != dt else out
 
@@ -141,13 +150,18 @@ class RingFlashAttentionCUDAFunction(Function):
     def backward(ctx, do: Tensor):
         ops = _ext.ops()
         (causal, window, ring_size, rank, layout, softclamp, scale, q_off, use_ring, d, d_pad, orig_dtype,
-         hk) = ctx.cfg
-        qp, o, lse, kv_gather, kbits = ctx.saved_tensors
+         hk, keep_gather) = ctx.cfg
+        qp, o, lse, kv_saved, kbits = ctx.saved_tensors
         kbits = kbits if kbits.numel() > 0 else None
         dt = qp.dtype
         b, n_q, h, _ = qp.shape
-        n_k = kv_gather.shape[3]
         dev = qp.device
+        if keep_gather:
+            kv_gather = kv_saved
+        else:  # memory-lean mode: rebuild the gather buffer around this rank's own slot
+            kv_gather = alloc_kv_buffer(ring_size, b, hk, kv_saved.shape[2], d_pad, dt, dev)
+            kv_gather[rank].copy_(kv_saved)
+        n_k = kv_gather.shape[3]
         pm = make_position_map(layout, ring_size, n_k)
         dop = _pad_head_dim(do.to(dt), d_pad).contiguous()
 
@@ -157,6 +171,7 @@ class RingFlashAttentionCUDAFunction(Function):
         _count()
 
         gather_done = None
+        kv_done = None
         if use_ring:
             ws = get_workspace(ring_size, dev)
             qdo_bytes = qdo_gather[rank].numel() * qdo_gather.element_size()
@@ -164,6 +179,11 @@ class RingFlashAttentionCUDAFunction(Function):
             stage, peer_ptrs = ws.staging("qdo", qdo_bytes + stat_bytes)
             stage[:qdo_bytes].copy_(qdo_gather[rank].view(torch.uint8).reshape(-1))
             stage[qdo_bytes:qdo_bytes + stat_bytes].copy_(stat_gather[rank].view(torch.uint8).reshape(-1))
+            kv_peer_ptrs = None
+            if not keep_gather:
+                kv_bytes = kv_gather[rank].numel() * kv_gather.element_size()
+                kv_stage, kv_peer_ptrs = ws.staging("kv", kv_bytes)
+                kv_stage.copy_(kv_gather[rank].view(torch.uint8).reshape(-1))
             ws.barrier()
             _count(3)
             main = torch.cuda.current_stream(dev)
@@ -172,6 +192,12 @@ class RingFlashAttentionCUDAFunction(Function):
             q_owners = ring_query_owners(pm, rank, causal, window)
             with torch.cuda.stream(ws.side_stream):
                 ws.side_stream.wait_event(start)
+                if kv_peer_ptrs is not None:  # K/V first: the dQ kernel is waiting for it
+                    for o_rank in ring_hop_owners(pm, rank, causal, window)[1:]:
+                        ops.peer_copy(kv_gather[o_rank], kv_peer_ptrs[o_rank], kv_bytes)
+                    kv_done = torch.cuda.Event()
+                    kv_done.record(ws.side_stream)
+                    kv_gather.record_stream(ws.side_stream)
                 for o_rank in q_owners[1:]:
                     ops.peer_copy(qdo_gather[o_rank], peer_ptrs[o_rank], qdo_bytes)
                     ops.peer_copy(stat_gather[o_rank], peer_ptrs[o_rank] + qdo_bytes, stat_bytes)
@@ -182,7 +208,9 @@ class RingFlashAttentionCUDAFunction(Function):
 
         common = (kbits, b, h, hk, rank, bool(causal), int(window or 0), float(scale), float(softclamp), pm.stride,
                   pm.seg_len, pm.base0, pm.base1, int(q_off))
-        # dQ only needs the K/V gather the forward already produced: it overlaps with the Q/dO gather
+        # dQ only needs the K/V gather (saved by the forward, or just re-pulled): it overlaps with the Q/dO gather
+        if kv_done is not None:
+            torch.cuda.current_stream(dev).wait_event(kv_done)
         dq = ops.attn_bwd_dq(qdo_gather, kv_gather, stat_gather, None, 0, *common,
                              ring_hop_owners(pm, rank, causal, window))
         if gather_done is not None:

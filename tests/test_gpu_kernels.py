@@ -144,8 +144,12 @@ def test_graft_smoke():
 # ------------------------------------------------------------------------------------------------
 # real multi-GPU ring (NVLink, symmetric memory) – needs >= 2 devices
 # ------------------------------------------------------------------------------------------------
-def _ring_worker(rank, world, layout, causal, hk, kmask=False):
+def _ring_worker(rank, world, layout, causal, hk, kmask=False, lean=False):
     import torch.distributed as dist
+
+    from ring_attention_pytorch_b200.ops import ring_cuda
+
+    ring_cuda.CONFIG["save_kv_gather"] = not lean
 
     from ring_attention_pytorch_b200.ops.oracle import attention_with_positions
     from ring_attention_pytorch_b200.ops.ring_cuda import ring_flash_attn_cuda
@@ -185,16 +189,19 @@ def _ring_worker(rank, world, layout, causal, hk, kmask=False):
     dist.barrier()
 
 
-@pytest.mark.parametrize("layout,causal,hk,kmask", [("plain", False, 4, False), ("striped", True, 2, False),
-                                                    ("zigzag", True, 4, False), ("plain", False, 2, True)])
-def test_real_ring_two_gpus(layout, causal, hk, kmask):
+@pytest.mark.parametrize("layout,causal,hk,kmask,lean", [("plain", False, 4, False, False),
+                                                         ("striped", True, 2, False, False),
+                                                         ("zigzag", True, 4, False, False),
+                                                         ("plain", False, 2, True, False),
+                                                         ("striped", True, 2, False, True)])
+def test_real_ring_two_gpus(layout, causal, hk, kmask, lean):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     from dist_utils import run_distributed
 
     world = min(torch.cuda.device_count(), 8)
     world = 2 if world < 4 else 4
-    run_distributed(_ring_worker, world, layout, causal, hk, kmask, backend="nccl")
+    run_distributed(_ring_worker, world, layout, causal, hk, kmask, lean, backend="nccl")
 
 
 # ------------------------------------------------------------------------------------------------
