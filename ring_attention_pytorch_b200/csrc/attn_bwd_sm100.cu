@@ -512,11 +512,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_cons
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
   if (warp >= 8) {  // control warps on the highest warp ids: the scheduler favours them
-    setmaxnreg_dec<72>();
+    setmaxnreg_dec<120>();
     if (warp == 8) dq_producer<D>(sm, p, &map_qd, &map_kv);
     if (warp == 9) dq_mma<D, BF16>(sm, p, tmem);
   } else {
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<192>();
     dq_softmax<D, BF16>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
   tc_fence_before();
@@ -937,11 +937,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
   if (warp >= 8) {  // control warps on the highest warp ids: the scheduler favours them
-    setmaxnreg_dec<72>();
+    setmaxnreg_dec<120>();
     if (warp == 8) dkv_producer<D>(sm, p, &map_qd64, &map_kv);
     if (warp == 9) dkv_mma<D, BF16>(sm, p, tmem);
   } else {
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<192>();
     dkv_softmax<D, BF16>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
   tc_fence_before();

@@ -581,7 +581,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const uint32_t tmem = sm.tmem_base;
 
   if (warp >= 8) {
-    setmaxnreg_dec<72>();
+    setmaxnreg_dec<120>();
     if (warp == 8) {
       producer_role<D>(sm, p, &map_q, &map_kv);
     } else if (warp == 9) {
@@ -590,7 +590,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (lane_id() == 0) fetch_role<D>(sm, p);
     }
   } else {
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<192>();
     softmax_role<D, BF16>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
 
