@@ -11,6 +11,7 @@ from ring_attention_pytorch_b200.models.ring_attention import (
     RMSNorm,
     apply_rotary_pos_emb,
 )
+from ring_attention_pytorch_b200.ops.flash_attn import flash_attn_backward, flash_attn_forward
 from ring_attention_pytorch_b200.ops.oracle import attention_with_positions, default_attention
 from ring_attention_pytorch_b200.ops.ring_flash_naive import ring_flash_attn, ring_flash_attn_
 from ring_attention_pytorch_b200.ops.tree_decode import tree_attn_decode
@@ -40,6 +41,8 @@ __all__ = [
     "ring_flash_attn_cuda",
     "ring_flash_attn_cuda_",
     "tree_attn_decode",
+    "flash_attn_forward",
+    "flash_attn_backward",
     "zig_zag_attn",
     "zig_zag_pad_seq",
     "zig_zag_shard",

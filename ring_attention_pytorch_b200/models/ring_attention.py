@@ -186,10 +186,34 @@ class RMSNorm(Module):
         return F.normalize(x, dim=-1) * self.scale * self.gamma
 
 
-def FeedForward(dim: int, mult: int = 4) -> nn.Sequential:
-    """reference ring_attention.py:479-486"""
+class BlockwiseSequential(nn.Sequential):
+    """``nn.Sequential`` applied to the sequence axis in blocks of ``chunk_size`` tokens, each block recomputed in
+    the backward (blockwise feed-forward of the Ring Attention paper, which the reference only draws in
+    ``ring.png``): the ``[b, n, 4 * dim]`` inner activation never exists for more than one block.  Child indices,
+    hence state-dict keys, are those of a plain ``nn.Sequential``."""
+
+    def __init__(self, *mods, chunk_size: Optional[int] = None):
+        super().__init__(*mods)
+        self.chunk_size = chunk_size
+
+    def forward(self, x: Tensor) -> Tensor:
+        run = super().forward
+        if not self.chunk_size or x.shape[-2] <= self.chunk_size:
+            return run(x)
+        if torch.is_grad_enabled() and x.requires_grad:
+            from torch.utils.checkpoint import checkpoint
+
+            outs = [checkpoint(run, c, use_reentrant=False) for c in x.split(self.chunk_size, dim=-2)]
+        else:
+            outs = [run(c) for c in x.split(self.chunk_size, dim=-2)]
+        return torch.cat(outs, dim=-2)
+
+
+def FeedForward(dim: int, mult: int = 4, chunk_size: Optional[int] = None) -> nn.Sequential:
+    """reference ring_attention.py:479-486; ``chunk_size`` (extra) makes it blockwise over the sequence."""
     dim_inner = int(dim * mult)
-    return nn.Sequential(RMSNorm(dim), nn.Linear(dim, dim_inner), nn.GELU(), nn.Linear(dim_inner, dim))
+    return BlockwiseSequential(RMSNorm(dim), nn.Linear(dim, dim_inner), nn.GELU(), nn.Linear(dim_inner, dim),
+                               chunk_size=chunk_size)
 
 
 class RingAttention(Module):
@@ -339,6 +363,7 @@ class RingTransformer(Module):
         ignore_index: int = -1,
         force_regular_attn: bool = False,
         use_cuda_kernel: Optional[bool] = None,
+        ff_chunk_size: Optional[int] = None,
     ):
         super().__init__()
         use_cuda_kernel = default(use_cuda_kernel, torch.cuda.is_available())
@@ -370,7 +395,7 @@ class RingTransformer(Module):
                               max_lookback_seq_len=layer_max_lookback_seq_len, striped_ring_attn=striped_ring_attn,
                               force_regular_attn=force_regular_attn, use_cuda_kernel=self.use_cuda_kernel,
                               auto_shard_seq=False),
-                FeedForward(dim=dim, mult=ff_mult),
+                FeedForward(dim=dim, mult=ff_mult, chunk_size=ff_chunk_size),
             ]))
         self.to_logits = nn.Sequential(RMSNorm(dim), nn.Linear(dim, num_tokens, bias=False))
         self.ignore_index = ignore_index

@@ -74,3 +74,114 @@ def test_lookback_window_matches_oracle():
     pos = torch.arange(40)
     ref = attention_with_positions(q, k, v, pos, pos, causal=True, window=7)
     assert torch.allclose(out, ref, atol=2e-6)
+
+
+# ---- single-hop building blocks (reference triton_flash_attn.py flash_attn_forward / flash_attn_backward) ----
+
+def _hop_inputs(b=2, n=37, h=4, hk=2, d=16, hops=3, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(b, n, h, d, generator=g)
+    ks = [torch.randn(b, n, hk, d, generator=g) for _ in range(hops)]
+    vs = [torch.randn(b, n, hk, d, generator=g) for _ in range(hops)]
+    return q, ks, vs
+
+
+@pytest.mark.parametrize("fp32_acc", [False, True])
+def test_hop_forward_carried_state_matches_dense(fp32_acc):
+    from ring_attention_pytorch_b200.ops.flash_attn import flash_attn_forward
+
+    q, ks, vs = _hop_inputs()
+    o = torch.zeros_like(q, dtype=torch.float32) if fp32_acc else None
+    m = lse = None
+    for hop, (k, v) in enumerate(zip(ks, vs)):
+        o, m, lse = flash_attn_forward(q, k, v, o=o, m=m, lse=lse, load_accumulated=hop > 0,
+                                       return_normalized_output=hop == len(ks) - 1)
+    ref, ref_lse = attention_with_positions(q, torch.cat(ks, 1), torch.cat(vs, 1), return_lse=True)
+    assert m.shape == (2, 4, 128) and lse.shape == (2, 4, 128)
+    assert torch.allclose(o, ref, atol=1e-5)
+    assert torch.allclose(lse[..., :37], ref_lse, atol=1e-5)
+
+
+def test_hop_forward_striped_diagonal_rule_and_bias():
+    """Two striped ranks emulated by hand: hop from the later rank masks the diagonal (reference
+    ring_flash_attention_cuda.py:157-160), key padding rides as an additive bias."""
+    from ring_attention_pytorch_b200.ops.flash_attn import flash_attn_forward
+
+    q, ks, vs = _hop_inputs(hops=2, seed=1)
+    n = q.shape[1]
+    # rank 0 of a 2-rank striped ring: own keys at positions 2j, peer keys at 2j + 1
+    o, m, lse = flash_attn_forward(q, ks[0], vs[0], causal=True, load_accumulated=False)
+    o, m, lse = flash_attn_forward(q, ks[1], vs[1], causal=True, causal_mask_diagonal=True, o=o, m=m, lse=lse,
+                                   return_normalized_output=True, remove_padding=True)
+    pos = torch.arange(n)
+    ref = attention_with_positions(q, torch.cat(ks, 1), torch.cat(vs, 1), 2 * pos, torch.cat([2 * pos, 2 * pos + 1]),
+                                   causal=True)
+    assert lse.shape[-1] == n
+    assert torch.allclose(o, ref, atol=1e-5)
+
+    keep = torch.rand(2, n, generator=torch.Generator().manual_seed(3)) > 0.4
+    keep[0] = False  # a batch row with every key dropped must give zeros, not NaN
+    bias = torch.where(keep, 0.0, -torch.finfo(torch.float32).max)
+    o2, _, _ = flash_attn_forward(q, ks[0], vs[0], bias=bias, load_accumulated=False, return_normalized_output=True)
+    ref2 = default_attention(q, ks[0], vs[0], keep)
+    assert torch.isfinite(o2).all() and torch.allclose(o2, ref2, atol=1e-5)
+    assert o2[0].abs().max() == 0
+
+
+@pytest.mark.parametrize("softclamp", [False, True])
+def test_hop_backward_accumulates_to_autograd(softclamp):
+    from ring_attention_pytorch_b200.ops.flash_attn import flash_attn_backward, flash_attn_forward
+
+    q, ks, vs = _hop_inputs(seed=2)
+    o = m = lse = None
+    for hop, (k, v) in enumerate(zip(ks, vs)):
+        o, m, lse = flash_attn_forward(q, k, v, causal=hop == 0, o=o, m=m, lse=lse, load_accumulated=hop > 0,
+                                       return_normalized_output=hop == len(ks) - 1, softclamp_qk_sim=softclamp,
+                                       softclamp_value=3.0)
+    do = torch.randn_like(o)
+    dq = torch.zeros_like(q)
+    dks, dvs = [], []
+    for hop, (k, v) in enumerate(zip(ks, vs)):
+        hq, hk_, hv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        delta = flash_attn_backward(do, q, k, v, o, lse, hq, hk_, hv, causal=hop == 0, softclamp_qk_sim=softclamp,
+                                    softclamp_value=3.0)
+        dq += hq
+        dks.append(hk_)
+        dvs.append(hv)
+    assert torch.allclose(delta[..., :q.shape[1]], (o * do).sum(-1).transpose(1, 2), atol=1e-5)
+
+    # oracle: hop 0 is causal on its own block, later hops are fully visible
+    n = q.shape[1]
+    qr = q.clone().requires_grad_()
+    kr = [k.clone().requires_grad_() for k in ks]
+    vr = [v.clone().requires_grad_() for v in vs]
+    h = q.shape[2]
+    from ring_attention_pytorch_b200.ops.oracle import expand_kv_heads, softclamp as clamp_fn
+    sim = torch.einsum("bihd,bjhd->bhij", qr, expand_kv_heads(torch.cat(kr, 1), h)) * q.shape[-1] ** -0.5
+    if softclamp:
+        sim = clamp_fn(sim, 3.0)
+    vis = torch.ones(n, 3 * n, dtype=torch.bool)
+    vis[:, :n] = torch.tril(torch.ones(n, n, dtype=torch.bool))
+    ref = torch.einsum("bhij,bjhd->bihd", sim.masked_fill(~vis, float("-inf")).softmax(-1),
+                       expand_kv_heads(torch.cat(vr, 1), h))
+    assert torch.allclose(o, ref, atol=1e-5)
+    ref.backward(do)
+    assert torch.allclose(dq, qr.grad, atol=2e-5)
+    for a, b_ in zip(dks + dvs, kr + vr):
+        assert torch.allclose(a, b_.grad, atol=2e-5)
+
+
+def test_blockwise_feedforward_matches_plain_and_shares_state_dict():
+    from ring_attention_pytorch_b200 import RingTransformer
+
+    torch.manual_seed(0)
+    kw = dict(num_tokens=64, dim=32, depth=2, causal=True, dim_head=8, heads=4, bucket_size=8, use_cuda_kernel=False)
+    plain, block = RingTransformer(**kw), RingTransformer(ff_chunk_size=5, **kw)
+    block.load_state_dict(plain.state_dict())          # identical parameter names
+    x = torch.randint(0, 64, (2, 23))
+    la, lb = plain(x, return_loss=True), block(x, return_loss=True)
+    la.backward()
+    lb.backward()
+    assert torch.allclose(la, lb, atol=1e-6)
+    for (na, pa), (nb, pb) in zip(plain.named_parameters(), block.named_parameters()):
+        assert na == nb and torch.allclose(pa.grad, pb.grad, atol=1e-5), na

@@ -390,3 +390,44 @@ def test_tree_decode_block_scaled_fp8_kv():
     out = tree_decode_cuda(q, k8, v8, dim_v=d, k_scale=ks, v_scale=vs, scale_block_keys=blk)
     ref = _dense_decode(q, kd, vd)
     assert (out.float() - ref).abs().max() < 3e-2
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_hop_api_kernel_path_matches_dense_path(d):
+    """flash_attn_forward / flash_attn_backward (reference triton_flash_attn.py:304, 988): the sm_100a kernels as
+    single-hop building blocks with carried (o, m, lse), vs the dense fp32 path of the same functions."""
+    from ring_attention_pytorch_b200.ops import flash_attn as fa
+
+    torch.manual_seed(0)
+    b, n, h, hk = 2, 300, 4, 2
+    q = torch.randn(b, n, h, d, device="cuda", dtype=torch.bfloat16)
+    ks = [torch.randn(b, n, hk, d, device="cuda", dtype=torch.bfloat16) for _ in range(3)]
+    vs = [torch.randn(b, n, hk, d, device="cuda", dtype=torch.bfloat16) for _ in range(3)]
+    keep = torch.rand(b, n, device="cuda") > 0.3
+    bias = torch.where(keep, 0.0, -torch.finfo(torch.float32).max)
+    # hop 0: causal incl. diagonal; hop 1: causal, diagonal masked (striped, later rank); hop 2: key padding
+    hop_kw = [dict(causal=True), dict(causal=True, causal_mask_diagonal=True), dict(bias=bias)]
+
+    def run(qq, kk, vv):
+        o = torch.zeros(b, n, h, d, device="cuda", dtype=torch.float32)
+        m = lse = None
+        for i, kw in enumerate(hop_kw):
+            o, m, lse = fa.flash_attn_forward(qq, kk[i], vv[i], o=o, m=m, lse=lse, load_accumulated=i > 0,
+                                              return_normalized_output=i == 2, **kw)
+        return o, lse
+
+    assert fa._use_kernel(q, True)
+    o_k, lse_k = run(q, ks, vs)
+    o_d, lse_d = run(q.float(), [t.float() for t in ks], [t.float() for t in vs])
+    assert (o_k - o_d).abs().max() < 3e-2
+    assert (lse_k[..., :n] - lse_d[..., :n]).abs().max() < 3e-2
+
+    do = torch.randn(b, n, h, d, device="cuda", dtype=torch.bfloat16)
+    for i, kw in enumerate(hop_kw):
+        got = [torch.empty_like(q), torch.empty_like(ks[i]), torch.empty_like(vs[i])]
+        want = [torch.empty_like(t, dtype=torch.float32) for t in got]
+        dl_k = fa.flash_attn_backward(do, q, ks[i], vs[i], o_d.to(q.dtype), lse_d, *got, **kw)
+        dl_d = fa.flash_attn_backward(do.float(), q.float(), ks[i].float(), vs[i].float(), o_d, lse_d, *want, **kw)
+        assert (dl_k - dl_d).abs().max() < 5e-2
+        for a, w in zip(got, want):
+            assert (a.float() - w).abs().max() / w.abs().max() < 4e-2, (i, kw.keys())
