@@ -543,6 +543,7 @@ struct DkvSmem {
   uint64_t kv_full, kv_empty;
   uint64_t qd_full[QSTAGES], qd_empty[QSTAGES];
   uint64_t sdp_full[2], pds_ready[2];
+  uint64_t s_full[2], s_free[2], dp_full[2];  // pipelined variant
   uint64_t acc_done, epi_done;
   uint32_t tmem_base;
 };
@@ -734,7 +735,262 @@ __device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, 
   }
 }
 
+// Pipelined issue order (PIPE = true).  Per stream w the TMEM blocks are X_w (S^T) and Y_w (dP^T, later P^T | dS^T
+// packed into its 64 columns).  X_w is free as soon as the warpgroup has pulled S^T(i) into registers (s_free), so
+// S^T(i+1) is computed while the warpgroup still works on tile i; dP^T(i+1) follows dV/dK(i) in the tensor pipe's FIFO
+// order (both touch Y_w).  The chain of one stream shrinks from  MMA -> softmax -> MMA  to  half a softmax -> MMA.
 template <int D, bool BF16>
+__device__ __forceinline__ void dkv_mma_pipe(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);
+  constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);
+  constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
+  constexpr uint64_t mnmaj64 = umma_smem_desc_hi_lo(SUB64, 1024, UMMA_LAYOUT_SW128);
+  const int lane = lane_id();
+  const uint32_t tmem = warp_uniform(tmem_in);
+  const uint32_t x_tm[2] = {tmem + 0, tmem + 128};
+  const uint32_t y_tm[2] = {tmem + 64, tmem + 192};
+  const uint32_t dk_tm = tmem + 256, dv_tm = tmem + 256 + D;
+
+  uint32_t n_item = 0, tile_base = 0;
+  // cumulative per-stream counters: tiles fetched, S^T issued, dP^T issued, dV/dK issued
+  uint32_t nf[2] = {0, 0}, iS[2] = {0, 0}, iP[2] = {0, 0}, iB[2] = {0, 0};
+  uint32_t jq[2][2] = {{0, 0}, {0, 0}};  // sequence number of the (at most two) tiles in flight per stream
+  const int total = dkv_num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
+    DkvItem it;
+    dkv_decode(p, idx, it);
+    mbar_wait(&sm.kv_full, n_item & 1, 900);
+    tc_fence_after();
+
+    StreamFeeder<DkvScan> feed;
+    dkv_init_scan(feed.scan, p, it);
+    bool end[2] = {false, false};
+    bool acc_started = false;
+    uint32_t ntiles = 0;
+    const uint64_t k_desc = umma_desc(kmaj, smem_u32(sm.k)), v_desc = umma_desc(kmaj, smem_u32(sm.v));
+    const uint64_t q_kdesc0 = umma_desc(kmaj, smem_u32(sm.q[0])), q_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.q[0]));
+    const uint64_t do_kdesc0 = umma_desc(kmaj, smem_u32(sm.dout[0])),
+                   do_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.dout[0]));
+    constexpr uint32_t STAGE16 = DkvSmem<D>::Q_TILE >> 4;
+    while (!(end[0] && end[1] && iB[0] == nf[0] && iB[1] == nf[1])) {
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        if (!end[w] && nf[w] - iB[w] < 2u) {
+          ScanTile tl;
+          uint32_t j = 0;
+          const int r = feed.fetch(w, lane, tl, j);
+          if (r == 1) {
+            jq[w][nf[w] & 1] = j;
+            nf[w]++;
+          } else if (r == -1) {
+            end[w] = true;
+          }
+        }
+        // dV += P^T dO, dK += dS^T Q   (tile iB)
+        if (iB[w] != iP[w] && warp_test(&sm.pds_ready[w], iB[w] & 1, lane)) {
+          if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 910);
+          tc_fence_after();
+          const uint32_t st = (tile_base + jq[w][iB[w] & 1]) % QSTAGES;
+          const uint64_t qmn = q_mndesc0 + uint64_t(st * STAGE16), domn = do_mndesc0 + uint64_t(st * STAGE16);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 64 / 16; ++kk) {
+              umma_ts(dv_tm, y_tm[w] + kk * 8, umma_desc_add(domn, kk * 2048), idesc_acc,
+                      (acc_started || kk > 0) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 64 / 16; ++kk) {
+              umma_ts(dk_tm, y_tm[w] + 32 + kk * 8, umma_desc_add(qmn, kk * 2048), idesc_acc,
+                      (acc_started || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&sm.qd_empty[st]);
+          }
+          __syncwarp();
+          acc_started = true;
+          iB[w]++;
+          ntiles++;
+        }
+        // dP^T = V dO^T   (tile iP; Y_w is free once dV/dK of the previous tile sit in front of it in the FIFO)
+        if (iP[w] != iS[w] && iP[w] == iB[w]) {
+          const uint32_t st = (tile_base + jq[w][iP[w] & 1]) % QSTAGES;
+          const uint64_t dok = do_kdesc0 + uint64_t(st * STAGE16);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+              const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+              umma_ss(y_tm[w], umma_desc_add(v_desc, offk), umma_desc_add(dok, offq), idesc_s, kk > 0);
+            }
+            umma_commit(&sm.dp_full[w]);
+          }
+          __syncwarp();
+          iP[w]++;
+        }
+        // S^T = K Q^T   (tile iS; needs its Q tile in smem and X_w drained into registers)
+        if (iS[w] != nf[w]) {
+          const uint32_t g = tile_base + jq[w][iS[w] & 1];
+          const uint32_t st = g % QSTAGES, ph = (g / QSTAGES) & 1;
+          const bool x_free = iS[w] == 0u || warp_test(&sm.s_free[w], (iS[w] - 1u) & 1, lane);
+          if (x_free && warp_test(&sm.qd_full[st], ph, lane)) {
+            tc_fence_after();
+            const uint64_t qk = q_kdesc0 + uint64_t(st * STAGE16);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < D / 16; ++kk) {
+                const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+                const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+                umma_ss(x_tm[w], umma_desc_add(k_desc, offk), umma_desc_add(qk, offq), idesc_s, kk > 0);
+              }
+              umma_commit(&sm.s_full[w]);
+            }
+            __syncwarp();
+            iS[w]++;
+          }
+        }
+      }
+    }
+    if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 911);
+    umma_commit_w(&sm.acc_done);
+    umma_commit_w(&sm.kv_empty);
+    tile_base += ntiles;
+  }
+}
+
+// Two-issuer variant (MODE 2).  Profiling the single-issuer kernels showed the MMA-issuing warp executing ~380
+// instructions of polling / bookkeeping per 128 x 64 step while the tensor pipe back-pressured it only 10 % of the time:
+// the issuer's own control flow, not the tensor core, paced the kernel.  Here the work is split by TMEM block instead of
+// by stream, which makes every wait a plain blocking mbarrier wait in program order (no state machine, no scanner in
+// the issuers, just the tile count of the item):
+//   warp 9  "S issuer"   : S^T(j) into X_w                       gated by qd_full(stage j), s_free[w]
+//   warp 10 "acc issuer" : dP^T(j) into Y_w, dV/dK(j) from Y_w   gated by qd_full(stage j), pds_ready[w]
+// The two warps never touch the same TMEM block, and only warp 10 accumulates into dK/dV, so no cross-warp ordering of
+// tcgen05.mma is relied upon.
+template <int D, bool BF16>
+__device__ __forceinline__ void dkv_issue_s(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);
+  constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
+  constexpr uint32_t STAGE16 = DkvSmem<D>::Q_TILE >> 4;
+  const int lane = lane_id();
+  const uint32_t tmem = warp_uniform(tmem_in);
+  uint32_t n_item = 0, tile_base = 0;
+  uint32_t c_s[2] = {0, 0};  // S^T issued per stream (cumulative): s_free parity
+  const int total = dkv_num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
+    DkvItem it;
+    dkv_decode(p, idx, it);
+    DkvScan scan;
+    dkv_init_scan(scan, p, it);
+    const uint32_t ntiles = scan.count(lane);
+    mbar_wait(&sm.kv_full, n_item & 1, 900);
+    tc_fence_after();
+    const uint64_t k_desc = umma_desc(kmaj, smem_u32(sm.k));
+    const uint64_t q_kdesc0 = umma_desc(kmaj, smem_u32(sm.q[0]));
+    for (uint32_t j = 0; j < ntiles; ++j) {
+      const uint32_t w = j & 1u;
+      const uint32_t g = tile_base + j;
+      const uint32_t st = g % QSTAGES, ph = (g / QSTAGES) & 1;
+      mbar_wait(&sm.qd_full[st], ph, 920 + st);
+      if (c_s[w] > 0) mbar_wait(&sm.s_free[w], (c_s[w] - 1u) & 1, 930 + w);
+      tc_fence_after();
+      const uint32_t x_tm = tmem + w * 128u;
+      const uint64_t qk = q_kdesc0 + uint64_t(st * STAGE16);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+          const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+          umma_ss(x_tm, umma_desc_add(k_desc, offk), umma_desc_add(qk, offq), idesc_s, kk > 0);
+        }
+        umma_commit(&sm.s_full[w]);
+      }
+      __syncwarp();
+      c_s[w]++;
+    }
+    umma_commit_w(&sm.kv_empty);  // second arrival comes from the acc issuer
+    tile_base += ntiles;
+  }
+}
+
+template <int D, bool BF16>
+__device__ __forceinline__ void dkv_issue_acc(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);
+  constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);
+  constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
+  constexpr uint64_t mnmaj64 = umma_smem_desc_hi_lo(SUB64, 1024, UMMA_LAYOUT_SW128);
+  constexpr uint32_t STAGE16 = DkvSmem<D>::Q_TILE >> 4;
+  const int lane = lane_id();
+  const uint32_t tmem = warp_uniform(tmem_in);
+  const uint32_t dk_tm = tmem + 256, dv_tm = tmem + 256 + D;
+  uint32_t n_item = 0, tile_base = 0;
+  uint32_t c_b[2] = {0, 0};  // dV/dK issued per stream (cumulative): pds_ready parity
+  const int total = dkv_num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
+    DkvItem it;
+    dkv_decode(p, idx, it);
+    DkvScan scan;
+    dkv_init_scan(scan, p, it);
+    const uint32_t ntiles = scan.count(lane);
+    mbar_wait(&sm.kv_full, n_item & 1, 901);
+    tc_fence_after();
+    const uint64_t v_desc = umma_desc(kmaj, smem_u32(sm.v));
+    const uint64_t do_kdesc0 = umma_desc(kmaj, smem_u32(sm.dout[0]));
+    const uint64_t q_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.q[0]));
+    const uint64_t do_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.dout[0]));
+
+    auto issue_dp = [&](uint32_t j) {  // dP^T(j) = V dO^T into Y_w (free: dV/dK(j-2) precede it in this warp's FIFO)
+      const uint32_t w = j & 1u;
+      const uint32_t g = tile_base + j;
+      const uint32_t st = g % QSTAGES, ph = (g / QSTAGES) & 1;
+      mbar_wait(&sm.qd_full[st], ph, 924 + st);
+      tc_fence_after();
+      const uint32_t y_tm = tmem + w * 128u + 64u;
+      const uint64_t dok = do_kdesc0 + uint64_t(st * STAGE16);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
+          const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
+          umma_ss(y_tm, umma_desc_add(v_desc, offk), umma_desc_add(dok, offq), idesc_s, kk > 0);
+        }
+        umma_commit(&sm.dp_full[w]);
+      }
+      __syncwarp();
+    };
+
+    if (ntiles > 0) issue_dp(0);
+    if (ntiles > 1) issue_dp(1);
+    for (uint32_t j = 0; j < ntiles; ++j) {
+      const uint32_t w = j & 1u;
+      const uint32_t st = (tile_base + j) % QSTAGES;
+      mbar_wait(&sm.pds_ready[w], c_b[w] & 1, 940 + w);
+      if (j == 0) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 910);
+      tc_fence_after();
+      const uint32_t y_tm = tmem + w * 128u + 64u;
+      const uint64_t qmn = q_mndesc0 + uint64_t(st * STAGE16), domn = do_mndesc0 + uint64_t(st * STAGE16);
+      const uint32_t acc0 = j > 0 ? 1u : 0u;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 64 / 16; ++kk) {
+          umma_ts(dv_tm, y_tm + kk * 8, umma_desc_add(domn, kk * 2048), idesc_acc, kk > 0 ? 1u : acc0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 64 / 16; ++kk) {
+          umma_ts(dk_tm, y_tm + 32 + kk * 8, umma_desc_add(qmn, kk * 2048), idesc_acc, kk > 0 ? 1u : acc0);
+        }
+        umma_commit(&sm.qd_empty[st]);
+      }
+      __syncwarp();
+      c_b[w]++;
+      if (j + 2 < ntiles) issue_dp(j + 2);
+    }
+    if (ntiles == 0) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 911);
+    umma_commit_w(&sm.acc_done);
+    umma_commit_w(&sm.kv_empty);
+    tile_base += ntiles;
+  }
+}
+
+template <int D, bool BF16, bool PIPE>
 __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem) {
   const int wg_tid = threadIdx.x - 128 * W;
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
@@ -768,14 +1024,24 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
       const uint32_t jj = jn++;
       if ((jj & 1u) != (uint32_t)W) continue;
       const uint32_t stg = (tile_base + jj) % QSTAGES;
-      mbar_wait((&sm.sdp_full[0] + W), cnt & 1, 1000 + W);
-      tc_fence_after();
       uint32_t sr[64], dp[64];
-      tmem_ld32(st_tm + 0, sr + 0);
-      tmem_ld32(st_tm + 32, sr + 32);
-      tc_wait_ld();
-      tmem_ld32(dpt_tm + 0, dp + 0);  // dP^T stays in flight while the exponentials below run
-      tmem_ld32(dpt_tm + 32, dp + 32);
+      if constexpr (PIPE) {
+        mbar_wait((&sm.s_full[0] + W), cnt & 1, 1000 + W);
+        tc_fence_after();
+        tmem_ld32(st_tm + 0, sr + 0);
+        tmem_ld32(st_tm + 32, sr + 32);
+        tc_wait_ld();
+        tc_fence_before();
+        mbar_arrive((&sm.s_free[0] + W));  // X_w may take S^T of this stream's next tile now
+      } else {
+        mbar_wait((&sm.sdp_full[0] + W), cnt & 1, 1000 + W);
+        tc_fence_after();
+        tmem_ld32(st_tm + 0, sr + 0);
+        tmem_ld32(st_tm + 32, sr + 32);
+        tc_wait_ld();
+        tmem_ld32(dpt_tm + 0, dp + 0);  // dP^T stays in flight while the exponentials below run
+        tmem_ld32(dpt_tm + 32, dp + 32);
+      }
 
       const int c0 = t.idx * 64;
       const float4* l4 = reinterpret_cast<const float4*>(sm.lse2[stg]);
@@ -801,6 +1067,12 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
           pw[q4 * 2] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
           pw[q4 * 2 + 1] = BF16 ? pack_bf16x2(p2, p3) : pack_f16x2(p2, p3);
         }
+        if constexpr (PIPE) {
+          mbar_wait((&sm.dp_full[0] + W), cnt & 1, 1004 + W);
+          tc_fence_after();
+          tmem_ld32(dpt_tm + 0, dp + 0);
+          tmem_ld32(dpt_tm + 32, dp + 32);
+        }
         tc_wait_ld();  // dP^T has landed
 #pragma unroll
         for (int q4 = 0; q4 < 16; ++q4) {
@@ -815,6 +1087,12 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
           dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(e23.x, e23.y) : pack_f16x2(e23.x, e23.y);
         }
       } else {
+        if constexpr (PIPE) {
+          mbar_wait((&sm.dp_full[0] + W), cnt & 1, 1004 + W);
+          tc_fence_after();
+          tmem_ld32(dpt_tm + 0, dp + 0);
+          tmem_ld32(dpt_tm + 32, dp + 32);
+        }
         tc_wait_ld();  // dP^T has landed
         const int split = p.pos.seg_len - c0;
         const int a0 = p.pos.base0[t.owner] + p.pos.stride * c0 + p.q_pos_offset;
@@ -859,8 +1137,13 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
           dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(dd[2], dd[3]) : pack_f16x2(dd[2], dd[3]);
         }
       }
-      tmem_st32(st_tm, pw);
-      tmem_st32(dpt_tm, dw);
+      if constexpr (PIPE) {  // P^T | dS^T share the dP^T block; the S^T block already belongs to the next tile
+        tmem_st32(dpt_tm, pw);
+        tmem_st32(dpt_tm + 32, dw);
+      } else {
+        tmem_st32(st_tm, pw);
+        tmem_st32(dpt_tm, dw);
+      }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive((&sm.pds_ready[0] + W));
@@ -906,7 +1189,7 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
   }
 }
 
-template <int D, bool BF16>
+template <int D, bool BF16, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_constant__ CUtensorMap map_kv,
                      const __grid_constant__ AttnBwdParams p) {
@@ -915,7 +1198,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
   const int warp = threadIdx.x / 32;
   if (threadIdx.x == 0) {
     mbar_init(&sm.kv_full, 1);
-    mbar_init(&sm.kv_empty, 1);
+    mbar_init(&sm.kv_empty, MODE == 2 ? 2 : 1);
     for (int i = 0; i < QSTAGES; ++i) {
       mbar_init(&sm.qd_full[i], 1);
       mbar_init(&sm.qd_empty[i], 1);
@@ -923,6 +1206,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.sdp_full[i], 1);
       mbar_init(&sm.pds_ready[i], 128);
+      mbar_init(&sm.s_full[i], 1);
+      mbar_init(&sm.s_free[i], 128);
+      mbar_init(&sm.dp_full[i], 1);
     }
     mbar_init(&sm.acc_done, 1);
     mbar_init(&sm.epi_done, 256);
@@ -939,10 +1225,17 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
   if (warp >= 8) {  // control warps on the highest warp ids: the scheduler favours them
     setmaxnreg_dec<120>();
     if (warp == 8) dkv_producer<D>(sm, p, &map_qd64, &map_kv);
-    if (warp == 9) dkv_mma<D, BF16>(sm, p, tmem);
+    if (warp == 9) {
+      if constexpr (MODE == 2) dkv_issue_s<D, BF16>(sm, p, tmem);
+      else if constexpr (MODE == 1) dkv_mma_pipe<D, BF16>(sm, p, tmem);
+      else dkv_mma<D, BF16>(sm, p, tmem);
+    }
+    if (warp == 10) {
+      if constexpr (MODE == 2) dkv_issue_acc<D, BF16>(sm, p, tmem);
+    }
   } else {
     setmaxnreg_inc<192>();
-    dkv_softmax<D, BF16>(sm, p, warp < 4 ? 0 : 1, tmem);
+    dkv_softmax<D, BF16, (MODE != 0)>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
   tc_fence_before();
   __syncthreads();
@@ -1018,7 +1311,17 @@ void launch_attn_bwd_dq(const CUtensorMap& map_qd, const CUtensorMap& map_kv, co
 template <int D>
 void launch_attn_bwd_dkdv(const CUtensorMap& map_qd64, const CUtensorMap& map_kv, const AttnBwdParams& p,
                           int num_sms, cudaStream_t stream) {
-  auto kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true> : attn_bwd_dkdv_kernel<D, false>;
+  // RAB_DKDV_PIPE: 0 = one issuer, S^T/dP^T together; 1 = one issuer, pipelined; 2 (default) = two issuers, see
+  // dkv_issue_s.  0 and 1 are kept for A/B measurements (n=65536, h=8: 22.9 / 22.3 / 15.2 ms).
+  static const int mode = [] {
+    const char* e = std::getenv("RAB_DKDV_PIPE");
+    return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? int(e[0] - '0') : 2;
+  }();
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const AttnBwdParams);
+  Kern kern;
+  if (mode == 2) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 2> : attn_bwd_dkdv_kernel<D, false, 2>;
+  else if (mode == 1) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 1> : attn_bwd_dkdv_kernel<D, false, 1>;
+  else kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 0> : attn_bwd_dkdv_kernel<D, false, 0>;
   const size_t smem = sizeof(DkvSmem<D>) + 1024;
   cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
              "bwd_dkdv smem attr");

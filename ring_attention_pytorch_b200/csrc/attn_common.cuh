@@ -130,6 +130,24 @@ struct WarpTileScan {
     }
   }
 
+  // Number of tiles next() will hand out.  Call on a freshly initialised scanner only (state is reset afterwards).
+  __device__ __forceinline__ uint32_t count(int lane) {
+    const int nt = (n_stream + tile - 1) / tile;
+    uint32_t c = 0;
+    for (s = 0; s < hop_count; ++s) {
+      for (base = 0; base < nt; base += 32) {
+        load_chunk(lane);
+        c += __popc(any);
+      }
+    }
+    s = 0;
+    base = 0;
+    any = 0;
+    rep = 0;
+    primed = false;
+    return c * (uint32_t)groups;
+  }
+
   __device__ __forceinline__ bool next(int lane, ScanTile& t) {
     const int nt = (n_stream + tile - 1) / tile;
     while (true) {

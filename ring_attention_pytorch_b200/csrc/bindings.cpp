@@ -85,6 +85,15 @@ void fill_posmap(rab::PosMap& pm, int64_t stride, int64_t seg_len, at::IntArrayR
   }
 }
 
+// cycles for `reps` back-to-back tcgen05.mma of one flavour on `ctas` SMs: returns [ctas, 2] (total, issue-side)
+Tensor umma_rate(int64_t mode, int64_t n, int64_t reps, int64_t alt, int64_t ctas) {
+  TORCH_CHECK(n == 64 || n == 128 || n == 256, "n must be 64, 128 or 256");
+  Tensor out = torch::zeros({ctas, 2}, torch::dtype(at::kLong).device(at::kCUDA));
+  rab::launch_umma_rate((int)mode, (int)n, (int)reps, (int)alt, (int)ctas,
+                        reinterpret_cast<long long*>(out.data_ptr<int64_t>()), at::cuda::getCurrentCUDAStream());
+  return out;
+}
+
 std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& kv_buf, at::IntArrayRef peer_ptrs,
                                     const Tensor& ready, const c10::optional<Tensor>& kmask_bits,
                                     int64_t kv_heads, int64_t rank, bool causal, int64_t window, double scale,
@@ -408,6 +417,7 @@ void symm_close(int64_t ptr) { rab::symm_close(reinterpret_cast<void*>(ptr)); }
 }  // namespace
 
 TORCH_LIBRARY(rab, m) {
+  m.def("umma_rate(int mode, int n, int reps, int alt, int ctas) -> Tensor");
   m.def("umma_probe(Tensor a, Tensor b, int mode, int n, int k, int idesc, int a_lbo, int a_sbo, int b_lbo, int "
         "b_sbo, int b_kstep) -> Tensor");
   m.def("attn_fwd(Tensor q, Tensor kv_buf, int[] peer_ptrs, Tensor ready, Tensor? kmask_bits, int kv_heads, int rank, "
@@ -443,6 +453,7 @@ TORCH_LIBRARY_IMPL(rab, CUDA, m) {
 }
 
 TORCH_LIBRARY_IMPL(rab, CompositeExplicitAutograd, m) {
+  m.impl("umma_rate", &umma_rate);
   m.impl("device_barrier", &device_barrier);
   m.impl("peer_copy", &peer_copy);
   m.impl("tree_decode_reduce", &tree_decode_reduce);

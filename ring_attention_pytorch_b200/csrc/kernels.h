@@ -25,6 +25,7 @@ struct ProbeParams {
 };
 void launch_umma_probe(const CUtensorMap& map_a, const CUtensorMap& map_b, const ProbeParams& p,
                        const void* a_raw, float* out, cudaStream_t stream);
+void launch_umma_rate(int mode, int n, int reps, int alt, int ctas, long long* out, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // position maps: how local index i on ring rank r maps to a global token position.

@@ -131,4 +131,116 @@ void launch_umma_probe(const CUtensorMap& map_a, const CUtensorMap& map_b, const
   cuda_check(cudaGetLastError(), "probe launch");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Issue-rate micro-benchmark: `reps` back-to-back tcgen05.mma (M = 128, K = 16 per instruction) of one operand
+// flavour, timed with clock64 from the first issue to the arrival of the final commit.  Used to calibrate the
+// tile-time models in BASELINE.md (which shapes are tensor-bound, which are shared-memory-operand-bound).
+//   mode 0: SS, B K-major      mode 1: SS, B MN-major      mode 2: TS (A in TMEM), B MN-major
+//   mode 3: TS, B K-major      alt != 0: alternate between two accumulators (two independent streams)
+// ------------------------------------------------------------------------------------------------
+struct RateSmem {
+  alignas(1024) uint8_t a[2 * 128 * 128];  // 128 rows x 128 k (two SW128 sub-tiles)
+  alignas(1024) uint8_t b[2 * 256 * 128];  // up to 256 rows x 128 k, or 128 k x 256 n
+  uint64_t bar;
+  uint32_t tmem_base;
+};
+
+template <int MODE, int N>
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int reps, int alt, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  RateSmem& sm = *reinterpret_cast<RateSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x / 32;
+  for (uint32_t i = threadIdx.x; i < sizeof(sm.a) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm.a)[i] = 0x3c003c00u;
+  for (uint32_t i = threadIdx.x; i < sizeof(sm.b) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm.b)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  {  // A operand for the TS modes: columns [448, 512)
+    uint32_t regs[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) regs[i] = 0x3c003c00u;
+    tmem_st32(tmem + 448 + (uint32_t(warp * 32) << 16), regs);
+    tmem_st32(tmem + 480 + (uint32_t(warp * 32) << 16), regs);
+    tc_wait_st();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {  // the whole warp runs the loop; one elected lane issues (the attention kernels' pattern)
+    constexpr bool b_mn = (MODE == 1 || MODE == 2);
+    constexpr bool a_tmem = (MODE >= 2);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N, 0, b_mn ? 1 : 0, 1);
+    const uint64_t a_desc0 = umma_desc(umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128), smem_u32(sm.a));
+    const uint64_t b_desc0 = b_mn ? umma_desc(umma_smem_desc_hi_lo(128 * 128, 1024, UMMA_LAYOUT_SW128), smem_u32(sm.b))
+                                  : umma_desc(umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128), smem_u32(sm.b));
+    const uint32_t d0 = warp_uniform(tmem), d1 = warp_uniform(tmem + (N <= 128 ? 192 : 0));
+    const uint32_t a_tm = warp_uniform(tmem + 448);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r += 8) {
+      const uint32_t d = (alt && (r & 8)) ? d1 : d0;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          constexpr uint32_t dummy = 0;
+          (void)dummy;
+          const uint32_t a_off = (kk / 4) * (128 * 128) + (kk % 4) * 32;
+          const uint32_t b_off = b_mn ? kk * 2048 : (kk / 4) * (N * 128) + (kk % 4) * 32;
+          if (a_tmem) {
+            umma_ts(d, a_tm + kk * 8, umma_desc_add(b_desc0, b_off), idesc, 1u);
+          } else {
+            umma_ss(d, umma_desc_add(a_desc0, a_off), umma_desc_add(b_desc0, b_off), idesc, 1u);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    umma_commit_w(&sm.bar);
+    mbar_wait(&sm.bar, 0, 3);
+    const long long t2 = clock64();
+    if (threadIdx.x == 0) {
+      out[blockIdx.x * 2] = t2 - t0;
+      out[blockIdx.x * 2 + 1] = t1 - t0;  // issue-side time
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int MODE, int N>
+static void launch_rate_one(int reps, int alt, int ctas, long long* out, cudaStream_t stream) {
+  const int smem = sizeof(RateSmem) + 1024;
+  cuda_check(cudaFuncSetAttribute(umma_rate_kernel<MODE, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+             "rate smem attr");
+  umma_rate_kernel<MODE, N><<<ctas, 128, smem, stream>>>(reps, alt, out);
+  cuda_check(cudaGetLastError(), "rate launch");
+}
+
+template <int MODE>
+static void launch_rate_mode(int n, int reps, int alt, int ctas, long long* out, cudaStream_t stream) {
+  if (n == 64) launch_rate_one<MODE, 64>(reps, alt, ctas, out, stream);
+  else if (n == 128) launch_rate_one<MODE, 128>(reps, alt, ctas, out, stream);
+  else launch_rate_one<MODE, 256>(reps, alt, ctas, out, stream);
+}
+
+void launch_umma_rate(int mode, int n, int reps, int alt, int ctas, long long* out, cudaStream_t stream) {
+  switch (mode) {
+    case 0: launch_rate_mode<0>(n, reps, alt, ctas, out, stream); break;
+    case 1: launch_rate_mode<1>(n, reps, alt, ctas, out, stream); break;
+    case 2: launch_rate_mode<2>(n, reps, alt, ctas, out, stream); break;
+    default: launch_rate_mode<3>(n, reps, alt, ctas, out, stream); break;
+  }
+}
+
 }  // namespace rab
