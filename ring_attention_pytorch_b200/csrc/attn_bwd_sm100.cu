@@ -51,6 +51,7 @@ struct DqSmem {
   uint64_t k_full[3], k_empty[3];
   uint64_t v_full[2], v_empty[2];
   uint64_t s_full[2], s_taken[2], dp_full[2], ds_ready[2];
+  uint64_t r_s_full[3], r_s_taken[3], r_dp_full[3], r_ds_ready[3], r_free[3];  // two-issuer variant: per TMEM region
   uint64_t dq_done, epi_done;
   uint32_t tmem_base;
 };
@@ -293,14 +294,131 @@ __device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, ui
   }
 }
 
+// Two-issuer variant of the dQ kernel (same reasoning as dkv_issue_s below: the single issuing warp's polling loop, not
+// the tensor pipe, paced the kernel).  The logits live in three rotating TMEM regions (tile g of this CTA's lifetime
+// uses region g % 3, which is also its K smem stage), every barrier between the issuers and the warpgroups is indexed
+// by region with parity (g / 3) & 1, and all waits are blocking waits in program order:
+//   warp 9  : S(j) = Q K^T into region r, dP(j) = dO V^T into region r once the warpgroup holds S(j) in registers
+//   warp 10 : dQ += dS(j) K with dS read from region r; frees the region and the K stage
+// A region is reused only after the dQ MMA that read it has completed, so no barrier can run two phases ahead.
+__device__ __forceinline__ uint32_t dq_region_col(uint32_t r) { return r == 0 ? 0u : (r == 1 ? 128u : 384u); }
+
 template <int D, bool BF16>
+__device__ __forceinline__ void dq_issue_sdp(DqSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0, BF16 ? 1 : 0);
+  constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
+  constexpr uint32_t SLOT16 = DqSmem<D>::TILE >> 4;
+  const int lane = lane_id();
+  const uint32_t tmem = warp_uniform(tmem_in);
+  uint32_t n_item = 0, tile_base = 0;
+  const int total = dq_num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
+    DqItem it;
+    dq_decode(p, idx, it);
+    DqScan scan;
+    dq_init_scan(scan, p, it);
+    const uint32_t ntiles = scan.count(lane);
+    mbar_wait(&sm.qdo_full, n_item & 1, 600);
+    tc_fence_after();
+    const uint64_t q_desc = umma_desc(kmaj, smem_u32(sm.q)), do_desc = umma_desc(kmaj, smem_u32(sm.dout));
+    const uint64_t k_kdesc0 = umma_desc(kmaj, smem_u32(sm.k[0])), v_kdesc0 = umma_desc(kmaj, smem_u32(sm.v[0]));
+
+    auto issue_s = [&](uint32_t j) {
+      const uint32_t g = tile_base + j;
+      const uint32_t r = g % 3, ph = (g / 3) & 1;
+      mbar_wait(&sm.k_full[r], ph, 620 + r);
+      if (g >= 3) mbar_wait(&sm.r_free[r], ph ^ 1, 630 + r);  // previous use of the region has been drained by dQ
+      tc_fence_after();
+      const uint32_t x_tm = tmem + dq_region_col(r);
+      const uint64_t kd = k_kdesc0 + uint64_t(r * SLOT16);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
+          umma_ss(x_tm, umma_desc_add(q_desc, off), umma_desc_add(kd, off), idesc_s, kk > 0);
+        }
+        umma_commit(&sm.r_s_full[r]);
+      }
+      __syncwarp();
+    };
+
+    if (ntiles > 0) issue_s(0);
+    if (ntiles > 1) issue_s(1);
+    for (uint32_t j = 0; j < ntiles; ++j) {
+      const uint32_t g = tile_base + j;
+      const uint32_t r = g % 3, ph = (g / 3) & 1, vs = g % 2, vph = (g / 2) & 1;
+      mbar_wait(&sm.v_full[vs], vph, 640 + vs);
+      mbar_wait(&sm.r_s_taken[r], ph, 650 + r);
+      tc_fence_after();
+      const uint32_t x_tm = tmem + dq_region_col(r);
+      const uint64_t vd = v_kdesc0 + uint64_t(vs * SLOT16);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
+          umma_ss(x_tm, umma_desc_add(do_desc, off), umma_desc_add(vd, off), idesc_s, kk > 0);
+        }
+        umma_commit(&sm.r_dp_full[r]);
+        umma_commit(&sm.v_empty[vs]);
+      }
+      __syncwarp();
+      if (j + 2 < ntiles) issue_s(j + 2);
+    }
+    umma_commit_w(&sm.qdo_empty);
+    tile_base += ntiles;
+  }
+}
+
+template <int D, bool BF16>
+__device__ __forceinline__ void dq_issue_dq(DqSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
+  constexpr uint32_t idesc_dq = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);
+  constexpr uint64_t mnmaj = umma_smem_desc_hi_lo(SUB128, 1024, UMMA_LAYOUT_SW128);
+  constexpr uint32_t SLOT16 = DqSmem<D>::TILE >> 4;
+  const int lane = lane_id();
+  const uint32_t tmem = warp_uniform(tmem_in);
+  const uint32_t dq_tm = tmem + 256;
+  uint32_t n_item = 0, tile_base = 0;
+  const int total = dq_num_items(p);
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
+    DqItem it;
+    dq_decode(p, idx, it);
+    DqScan scan;
+    dq_init_scan(scan, p, it);
+    const uint32_t ntiles = scan.count(lane);
+    const uint64_t k_mndesc0 = umma_desc(mnmaj, smem_u32(sm.k[0]));
+    for (uint32_t j = 0; j < ntiles; ++j) {
+      const uint32_t g = tile_base + j;
+      const uint32_t r = g % 3, ph = (g / 3) & 1;
+      mbar_wait(&sm.r_ds_ready[r], ph, 660 + r);
+      if (j == 0) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 610);
+      tc_fence_after();
+      const uint32_t x_tm = tmem + dq_region_col(r);
+      const uint64_t kmn = k_mndesc0 + uint64_t(r * SLOT16);
+      const uint32_t acc0 = j > 0 ? 1u : 0u;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 128 / 16; ++kk) {
+          umma_ts(dq_tm, x_tm + kk * 8, umma_desc_add(kmn, kk * 2048), idesc_dq, kk > 0 ? 1u : acc0);
+        }
+        umma_commit(&sm.k_empty[r]);
+        umma_commit(&sm.r_free[r]);
+      }
+      __syncwarp();
+    }
+    if (ntiles == 0) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 611);
+    umma_commit_w(&sm.dq_done);
+    tile_base += ntiles;
+  }
+}
+
+template <int D, bool BF16, bool TWO>
 __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem) {
   const int wg_tid = threadIdx.x - 128 * W;
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
-  const uint32_t x_tm = tmem + W * 128 + lane_off;
+  uint32_t x_tm = tmem + W * 128 + lane_off;
   const uint32_t dq_tm = tmem + 256 + lane_off;
   const int lane = lane_id();
-  uint32_t cnt = 0, n_item = 0;
+  uint32_t cnt = 0, n_item = 0, tile_base = 0;
 
   const bool clamp = p.softclamp > 0.f;
   const float mul = clamp ? 1.f : p.scale * kLog2e;
@@ -326,8 +444,28 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
     ScanTile t;
     uint32_t jj = 0;
     while (scan.next(lane, t)) {
-      if (((jj++) & 1u) != (uint32_t)W) continue;
-      mbar_wait((&sm.s_full[0] + W), cnt & 1, 700 + W);
+      const uint32_t jcur = jj++;
+      if ((jcur & 1u) != (uint32_t)W) continue;
+      // barriers of this tile: per stream (parity = tiles done by this warpgroup) or, with two issuers, per region
+      uint64_t *b_s_full, *b_s_taken, *b_dp_full, *b_ds_ready;
+      uint32_t bpar;
+      if constexpr (TWO) {
+        const uint32_t g = tile_base + jcur;
+        const uint32_t r = g % 3;
+        bpar = (g / 3) & 1;
+        x_tm = tmem + dq_region_col(r) + lane_off;
+        b_s_full = &sm.r_s_full[r];
+        b_s_taken = &sm.r_s_taken[r];
+        b_dp_full = &sm.r_dp_full[r];
+        b_ds_ready = &sm.r_ds_ready[r];
+      } else {
+        bpar = cnt & 1;
+        b_s_full = &sm.s_full[0] + W;
+        b_s_taken = &sm.s_taken[0] + W;
+        b_dp_full = &sm.dp_full[0] + W;
+        b_ds_ready = &sm.ds_ready[0] + W;
+      }
+      mbar_wait(b_s_full, bpar, 700 + W);
       tc_fence_after();
       uint32_t sr[128];
       tmem_ld32(x_tm + 0, sr + 0);
@@ -336,7 +474,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
       tmem_ld32(x_tm + 96, sr + 96);
       tc_wait_ld();
       tc_fence_before();
-      mbar_arrive((&sm.s_taken[0] + W));
+      mbar_arrive(b_s_taken);
 
       if (t.part[0]) {
         const int c0 = t.idx * 128;
@@ -372,7 +510,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
           sr[j + 1] = __float_as_uint(fast_exp2(a.y));
         }
       }
-      mbar_wait((&sm.dp_full[0] + W), cnt & 1, 710 + W);
+      mbar_wait(b_dp_full, bpar, 710 + W);
       tc_fence_after();
       // dS = P o (dP - delta) [* (1 - tanh^2) with softclamp]; the softmax scale is folded into the epilogue.
       if (!clamp) {
@@ -437,9 +575,10 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
       }
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive((&sm.ds_ready[0] + W));
+      mbar_arrive(b_ds_ready);
       cnt++;
     }
+    tile_base += jj;
 
     // epilogue: warpgroup W converts columns [W*D/2, (W+1)*D/2) of dQ
     mbar_wait(&sm.dq_done, n_item & 1, 720 + W);
@@ -477,7 +616,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
   }
 }
 
-template <int D, bool BF16>
+template <int D, bool BF16, bool TWO>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_constant__ CUtensorMap map_kv,
                    const __grid_constant__ AttnBwdParams p) {
@@ -499,6 +638,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_cons
       mbar_init(&sm.dp_full[i], 1);
       mbar_init(&sm.ds_ready[i], 128);
     }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&sm.r_s_full[i], 1);
+      mbar_init(&sm.r_s_taken[i], 128);
+      mbar_init(&sm.r_dp_full[i], 1);
+      mbar_init(&sm.r_ds_ready[i], 128);
+      mbar_init(&sm.r_free[i], 1);
+    }
     mbar_init(&sm.dq_done, 1);
     mbar_init(&sm.epi_done, 256);
     fence_mbar_init();
@@ -514,10 +660,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_cons
   if (warp >= 8) {  // control warps on the highest warp ids: the scheduler favours them
     setmaxnreg_dec<120>();
     if (warp == 8) dq_producer<D>(sm, p, &map_qd, &map_kv);
-    if (warp == 9) dq_mma<D, BF16>(sm, p, tmem);
+    if (warp == 9) {
+      if constexpr (TWO) dq_issue_sdp<D, BF16>(sm, p, tmem);
+      else dq_mma<D, BF16>(sm, p, tmem);
+    }
+    if (warp == 10) {
+      if constexpr (TWO) dq_issue_dq<D, BF16>(sm, p, tmem);
+    }
   } else {
     setmaxnreg_inc<192>();
-    dq_softmax<D, BF16>(sm, p, warp < 4 ? 0 : 1, tmem);
+    dq_softmax<D, BF16, TWO>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
   tc_fence_before();
   __syncthreads();
@@ -1299,7 +1451,14 @@ __global__ void bwd_prep_kernel(const uint16_t* __restrict__ q, const uint16_t* 
 template <int D>
 void launch_attn_bwd_dq(const CUtensorMap& map_qd, const CUtensorMap& map_kv, const AttnBwdParams& p, int num_sms,
                         cudaStream_t stream) {
-  auto kern = p.is_bf16 ? attn_bwd_dq_kernel<D, true> : attn_bwd_dq_kernel<D, false>;
+  // default: two issuing warps + three rotating TMEM regions (see dq_issue_sdp); RAB_DQ_TWO=0: single polling issuer
+  // (kept for A/B measurements: 13.1 -> 11.8 ms at n=65536, h=8)
+  static const bool two = [] {
+    const char* e = std::getenv("RAB_DQ_TWO");
+    return e == nullptr || e[0] != '0';
+  }();
+  auto kern = two ? (p.is_bf16 ? attn_bwd_dq_kernel<D, true, true> : attn_bwd_dq_kernel<D, false, true>)
+                  : (p.is_bf16 ? attn_bwd_dq_kernel<D, true, false> : attn_bwd_dq_kernel<D, false, false>);
   const size_t smem = sizeof(DqSmem<D>) + 1024;
   cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "bwd_dq smem attr");
   const int items = p.batch * p.heads * ((p.n_q + 127) / 128);
