@@ -423,6 +423,25 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for two values on the FMA pipe: round-to-nearest split x = n + f (magic-number add), degree-3 minimax polynomial
+// for 2^f on [-0.5, 0.5] (relative error 1.2e-4, p(0) == 1 exactly), 2^n added into the exponent field.  Takes a share of
+// the softmax exponentials off the MUFU (16 ex2 / clk / SM, the unit that ties with the tensor core in the forward).
+// -inf (masked logits) returns exactly 0; valid for x < 128.
+__device__ __forceinline__ float2 poly_exp2x2(float2 x) {
+  x.x = fmaxf(x.x, -127.f);
+  x.y = fmaxf(x.y, -127.f);
+  const float2 t = fadd2(x, make_float2(12582912.f, 12582912.f));  // 1.5 * 2^23: low mantissa bits hold n
+  const float2 nf = fadd2(t, make_float2(-12582912.f, -12582912.f));
+  const float2 fr = fadd2(x, make_float2(-nf.x, -nf.y));
+  float2 pl = ffma2(make_float2(0.05536489188671112f, 0.05536489188671112f), fr,
+                    make_float2(0.24221116304397583f, 0.24221116304397583f));
+  pl = ffma2(pl, fr, make_float2(0.6932103037834167f, 0.6932103037834167f));
+  pl = ffma2(pl, fr, make_float2(1.f, 1.f));
+  float2 r;
+  r.x = __uint_as_float(__float_as_uint(pl.x) + (__float_as_uint(t.x) << 23));
+  r.y = __uint_as_float(__float_as_uint(pl.y) + (__float_as_uint(t.y) << 23));
+  return r;
+}
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

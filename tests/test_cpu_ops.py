@@ -185,3 +185,29 @@ def test_blockwise_feedforward_matches_plain_and_shares_state_dict():
     assert torch.allclose(la, lb, atol=1e-6)
     for (na, pa), (nb, pb) in zip(plain.named_parameters(), block.named_parameters()):
         assert na == nb and torch.allclose(pa.grad, pb.grad, atol=1e-5), na
+
+
+def test_poly_exp2_reference():
+    """Host emulation (fp32 op by op) of ``poly_exp2x2`` in csrc/ptx.cuh, the FMA-pipe exponential the forward kernel
+    can use for a share of its softmax (RAB_FWD_EXP_POLY): relative error < 1.5e-4, masked logits give exactly 0."""
+    import numpy as np
+
+    c = np.array([1.0, 0.6932103037834167, 0.24221116304397583, 0.05536489188671112], dtype=np.float32)
+
+    def poly_exp2(x):
+        x = np.maximum(x.astype(np.float32), np.float32(-127.0))
+        magic = np.float32(12582912.0)
+        t = (x + magic).astype(np.float32)
+        nf = (t - magic).astype(np.float32)
+        fr = (x - nf).astype(np.float32)
+        p = (c[3] * fr + c[2]).astype(np.float32)
+        p = (p * fr + c[1]).astype(np.float32)
+        p = (p * fr + c[0]).astype(np.float32)
+        eb = (t.view(np.uint32) << np.uint32(23)).astype(np.uint32)
+        return (p.view(np.uint32) + eb).astype(np.uint32).view(np.float32)
+
+    x = np.linspace(-40, 8, 400001).astype(np.float32)
+    got, ref = poly_exp2(x), np.exp2(x.astype(np.float64))
+    assert np.max(np.abs(got - ref) / ref) < 1.5e-4
+    special = poly_exp2(np.array([-np.inf, -1000.0, 0.0], dtype=np.float32))
+    assert special[0] == 0.0 and special[1] == 0.0 and special[2] == 1.0
