@@ -129,7 +129,7 @@ def split_by_rank(x, group=None):
     """reference distributed.py:117-127 — pick element ``rank`` of a tuple of per-rank pieces."""
     rank = dist.get_rank(group)
     out = x[rank]
-    if isinstance(x, tuple):
+    if isinstance(x, (tuple, list)):
         sizes = tuple(map(lambda t: t.shape[0], x))
     else:
         sizes = (x.shape[1],) * x.shape[0]

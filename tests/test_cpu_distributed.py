@@ -239,3 +239,49 @@ def _allgather_worker(rank, world):
 
 def test_all_gather_backward_is_reduce_scatter():
     run_distributed(_allgather_worker, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# ring helpers (reference ring.py) with ring sets: world 4 = 2 ring sets x ring size 2
+# ------------------------------------------------------------------------------------------------
+def _ring_helper_worker(rank, world, ring_size):
+    from ring_attention_pytorch_b200.parallel.distributed import all_gather_variable_dim, split_by_rank
+    from ring_attention_pytorch_b200.parallel.ring import (all_ring_pass, circular_rank_left, circular_rank_right,
+                                                            null_ring_pass, one_ring_pass, ring_pass)
+
+    ring_set, local = divmod(rank, ring_size)
+    base = ring_set * ring_size
+    assert circular_rank_right(ring_size=ring_size) == base + (local + 1) % ring_size
+    assert circular_rank_left(ring_size=ring_size) == base + (local - 1) % ring_size
+
+    x = torch.full((3,), float(rank))
+    for num in range(0, ring_size + 1):
+        got, sent = ring_pass(num, x.clone(), None, ring_size)
+        src = base + (local - num) % ring_size  # data moves `num` positions to the right inside the ring set
+        assert torch.equal(got, torch.full((3,), float(src))), (rank, num, got)
+        assert torch.equal(sent, x)
+    got, _ = one_ring_pass(x.clone(), None, ring_size)
+    assert got[0].item() == base + (local - 1) % ring_size
+
+    seen = []
+    for info, ((t, none), _) in all_ring_pass(x.clone(), None, ring_size=ring_size):
+        assert none is None
+        seen.append((info.ring_rank, int(t[0].item()), info.iter_info))
+    # the tensor held at step s was produced by the ring-local rank (local - s), of this ring set
+    assert [s[0] for s in seen] == [(local - s) % ring_size for s in range(ring_size)]
+    assert [s[1] for s in seen] == [base + (local - s) % ring_size for s in range(ring_size)]
+    assert seen[0][2] == (True, ring_size == 1) and seen[-1][2] == (ring_size == 1, True)
+    limited = list(all_ring_pass(x.clone(), max_iters=1, ring_size=ring_size))
+    assert len(limited) == 1 and limited[0][0].iter_info == (True, True)
+    assert len(list(null_ring_pass(x))) == 1
+
+    # variable-size gather + split_by_rank round trip
+    y = torch.full((rank + 1, 2), float(rank))
+    gathered, sizes = all_gather_variable_dim(y, dim=0)
+    assert sizes.tolist() == [r + 1 for r in range(world)] and gathered.shape[0] == sum(range(1, world + 1))
+    mine, piece_sizes = split_by_rank(gathered.split(sizes.tolist(), dim=0))
+    assert torch.equal(mine, y) and piece_sizes.tolist() == sizes.tolist()
+
+
+def test_ring_helpers_with_ring_sets():
+    run_distributed(_ring_helper_worker, 4, 2)
