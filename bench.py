@@ -235,26 +235,67 @@ def main():
         hq = torch.randn(B, n, H, D, dtype=dt).pin_memory()
         hk = torch.randn(B, n, HK, D, dtype=dt).pin_memory()
         hv = torch.randn(B, n, HK, D, dtype=dt).pin_memory()
-        dq_, dk_, dv_ = (torch.empty_like(t_, device=dev) for t_ in (hq, hk, hv))
+        host = (hq, hk, hv)
 
-        def e2e_step():
-            dq_.copy_(hq, non_blocking=True)
-            dk_.copy_(hk, non_blocking=True)
-            dv_.copy_(hv, non_blocking=True)
-            qq, kk, vv = (t_.detach().requires_grad_() for t_ in (dq_, dk_, dv_))
-            out = attn(qq, kk, vv)
-            loss = (out * w).sum(dtype=torch.float32)
-            loss.backward()
-            return float(loss.item())  # device -> host read of the step's result
+        def run_e2e(prefetch: bool, nsteps: int) -> float:
+            """nsteps end-to-end steps; returns elapsed ms on the device.  Every step's inputs are copied from pinned
+            host memory inside the timed region and its loss is read back.  With ``prefetch`` the copy of step i+1 runs
+            on a copy stream into the other device buffer while step i computes (what a prefetching data loader does);
+            without it the copy is serial on the compute stream."""
+            main = torch.cuda.current_stream(dev)
+            nbuf = 2 if prefetch else 1
+            bufs = [tuple(torch.empty_like(t_, device=dev) for t_ in host) for _ in range(nbuf)]
+            copy_stream = torch.cuda.Stream(device=dev) if prefetch else main
+            ready = [torch.cuda.Event() for _ in range(nbuf)]
+            free = [torch.cuda.Event() for _ in range(nbuf)]
 
-        e2e_step()
-        sync()
-        e0.record()
-        for _ in range(args.steps):
-            e2e_step()
-        e1.record()
-        sync()
-        ems = e0.elapsed_time(e1)
+            def issue_copy(i):
+                b = i % nbuf
+                with torch.cuda.stream(copy_stream):
+                    if prefetch:
+                        copy_stream.wait_event(free[b])  # the step that last read this buffer is done (no-op at first)
+                    for d_, h_ in zip(bufs[b], host):
+                        d_.copy_(h_, non_blocking=True)
+                    if prefetch:
+                        ready[b].record(copy_stream)
+
+            def compute(i):
+                b = i % nbuf
+                if prefetch:
+                    main.wait_event(ready[b])
+                qq, kk, vv = (t_.detach().requires_grad_() for t_ in bufs[b])
+                out = attn(qq, kk, vv)
+                loss = (out * w).sum(dtype=torch.float32)
+                loss.backward()
+                if prefetch:
+                    free[b].record(main)
+                return float(loss.item())  # device -> host read of the step's result
+
+            sync()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            issue_copy(0)
+            for i in range(nsteps):
+                if prefetch and i + 1 < nsteps:
+                    issue_copy(i + 1)
+                compute(i)
+                if not prefetch and i + 1 < nsteps:
+                    issue_copy(i + 1)
+            s1.record()
+            sync()
+            return s0.elapsed_time(s1)
+
+        pipeline, ems = "double-buffered H2D prefetch on a copy stream", None
+        try:
+            run_e2e(True, 1)  # untimed warm-up of the e2e path
+            ems = run_e2e(True, args.steps)
+        except Exception as e:  # noqa: BLE001 - fall back to the serial loop rather than lose the number
+            print(f"[bench] prefetching e2e loop failed ({type(e).__name__}: {e}); using the serial loop", file=sys.stderr)
+        if ems is None:  # outside the except block so the failed attempt's buffers are released first
+            pipeline = "serial H2D on the compute stream"
+            torch.cuda.empty_cache()
+            run_e2e(False, 1)
+            ems = run_e2e(False, args.steps)
         t = torch.tensor([ems], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -266,6 +307,7 @@ def main():
             "ms_per_step": ems / args.steps,
             "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": 4 * world,
+            "pipeline": pipeline,
         }
 
     if rank == 0:
