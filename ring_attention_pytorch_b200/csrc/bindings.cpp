@@ -36,14 +36,24 @@ Tensor umma_probe(const Tensor& a, const Tensor& b, int64_t mode, int64_t n, int
   check_16bit(a, "a");
   check_16bit(b, "b");
   TORCH_CHECK(a.is_contiguous() && b.is_contiguous());
-  TORCH_CHECK(a.size(0) == 128 && a.size(1) == k);
   c10::cuda::CUDAGuard guard(a.device());
-  uint64_t adims[2] = {(uint64_t)k, 128};
-  uint64_t astr[1] = {(uint64_t)k * 2};
-  uint32_t abox[2] = {64, 128};
-  CUtensorMap map_a = rab::make_tmap_bf16(a.data_ptr(), 2, adims, astr, abox, rab::TmapSwizzle::B128);
-  CUtensorMap map_b;
-  if (mode == 0) {
+  CUtensorMap map_a, map_b;
+  if (mode == 3) {  // a is At [k, 128] (MN-major A); b [k, 64] is written to shared memory by the kernel's threads
+    TORCH_CHECK(a.size(0) == k && a.size(1) == 128 && b.size(0) == k && b.size(1) == 64 && n == 64);
+    uint64_t adims[2] = {128, (uint64_t)k};
+    uint64_t astr[1] = {128 * 2};
+    uint32_t abox[2] = {64, (uint32_t)k};
+    map_a = rab::make_tmap_bf16(a.data_ptr(), 2, adims, astr, abox, rab::TmapSwizzle::B128);
+    map_b = map_a;
+  } else {
+    TORCH_CHECK(a.size(0) == 128 && a.size(1) == k);
+    uint64_t adims[2] = {(uint64_t)k, 128};
+    uint64_t astr[1] = {(uint64_t)k * 2};
+    uint32_t abox[2] = {64, 128};
+    map_a = rab::make_tmap_bf16(a.data_ptr(), 2, adims, astr, abox, rab::TmapSwizzle::B128);
+  }
+  if (mode == 3) {
+  } else if (mode == 0) {
     TORCH_CHECK(b.size(0) == n && b.size(1) == k);
     uint64_t bdims[2] = {(uint64_t)k, (uint64_t)n};
     uint64_t bstr[1] = {(uint64_t)k * 2};
@@ -67,7 +77,8 @@ Tensor umma_probe(const Tensor& a, const Tensor& b, int64_t mode, int64_t n, int
   p.b_sbo = (uint32_t)b_sbo;
   p.b_kstep_bytes = (uint32_t)b_kstep;
   Tensor out = torch::empty({128, n}, a.options().dtype(at::kFloat));
-  rab::launch_umma_probe(map_a, map_b, p, a.data_ptr(), out.data_ptr<float>(), at::cuda::getCurrentCUDAStream());
+  rab::launch_umma_probe(map_a, map_b, p, mode == 3 ? b.data_ptr() : a.data_ptr(), out.data_ptr<float>(),
+                         at::cuda::getCurrentCUDAStream());
   return out;
 }
 

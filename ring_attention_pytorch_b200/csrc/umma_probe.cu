@@ -5,6 +5,9 @@
 //   mode 1: D = A * B     A[128][K] K-major (smem), B[K][N] MN-major (smem)          (O = P V, SS form)
 //   mode 2: D = A * B     A[128][K] from TMEM (packed 16-bit, written with tcgen05.st), B[K][N] MN-major
 //                                                                                    (O = P V, TS form)
+//   mode 3: D = A * B     A given transposed, At[K][128] (MN-major A, TMA-loaded like a V tile), B[K][64] MN-major
+//                         written to shared memory BY THE THREADS with the 128B swizzle applied by hand and made
+//                         visible to the tensor core with fence.proxy.async (dQ^T = K^T dS^T of a one-kernel backward)
 // A and B tiles are brought in with 128B-swizzled TMA boxes of 64 elements x rows, exactly the way the
 // attention kernels stage Q/K/V.
 #include "kernels.h"
@@ -47,13 +50,21 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (tid == 0) {
     // A: [128 rows][K] with K contiguous; one box per 64-wide k sub-tile.
     uint32_t bytes = 0;
-    if (p.mode != 2) {
+    if (p.mode == 3) {
+      // At: [K rows][128], one box of 64 (m) x K rows per 64-wide m sub-tile
+      for (int s = 0; s < 2; ++s) {
+        tma_load_2d(sm.a[s], &map_a, &sm.bar_load, s * 64, 0);
+        bytes += p.k * 128;
+      }
+    } else if (p.mode != 2) {
       for (int s = 0; s < p.k / 64; ++s) {
         tma_load_2d(sm.a[s], &map_a, &sm.bar_load, s * 64, 0);
         bytes += 128 * 128;
       }
     }
-    if (p.mode == 0) {
+    if (p.mode == 3) {
+      // B is written by the threads below
+    } else if (p.mode == 0) {
       // B: [N rows][K], box = 64 (k) x N rows
       for (int s = 0; s < p.k / 64; ++s) {
         tma_load_2d(sm.b[s], &map_b, &sm.bar_load, s * 64, 0);
@@ -81,6 +92,17 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     tc_wait_st();
     tc_fence_before();
   }
+  if (p.mode == 3) {
+    // thread r owns row r of B[K][64] (64 16-bit values = eight 16-byte chunks); chunk c of row r lives at chunk
+    // position c ^ (r % 8) of the 128-byte row: the layout a 128B-swizzled TMA box would have produced
+    if (tid < p.k) {
+      const uint4* src = reinterpret_cast<const uint4*>(a_raw + (size_t)tid * 64);
+      uint8_t* row = sm.b[0] + tid * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + ((c ^ (tid & 7)) << 4)) = src[c];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __syncthreads();
   tc_fence_after();
 
@@ -98,6 +120,9 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       if (p.mode == 2) {
         umma_ts(d_tmem, a_tmem + kk * 8, bdesc, p.idesc, kk > 0);
+      } else if (p.mode == 3) {
+        const uint64_t adesc = umma_desc(a_static, smem_u32(sm.a[0]) + kk * p.b_kstep_bytes);
+        umma_ss(d_tmem, adesc, bdesc, p.idesc, kk > 0);
       } else {
         const uint64_t adesc = umma_desc(a_static, smem_u32(sm.a[kk / 4]) + (kk % 4) * 32);
         umma_ss(d_tmem, adesc, bdesc, p.idesc, kk > 0);

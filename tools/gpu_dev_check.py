@@ -56,6 +56,26 @@ def case_probe(mode: int, variant: str = "base"):
     return {"max_abs_err": err, "rel": rel, "ok": rel < 2e-2}
 
 
+def case_probe_mn_a(k: int = 128):
+    """Not validated yet (written after the last GPU minute of round 1): MN-major A from shared memory plus a B tile
+    written by the threads with a hand-applied 128B swizzle — the two operand flavours a one-kernel (5-GEMM) backward
+    needs for dQ^T = K^T dS^T.  Run with ``--only xprobe_mn_a``."""
+    import torch
+    from ring_attention_pytorch_b200.ops import _ext
+
+    ops = _ext.ops()
+    torch.manual_seed(0)
+    at = torch.randn(k, 128, device="cuda", dtype=torch.bfloat16)   # A^T: [K][M]
+    b = torch.randn(k, 64, device="cuda", dtype=torch.bfloat16)     # B:   [K][N]
+    ref = at.float().t() @ b.float()
+    idesc = _idesc(128, 64, 1, 1)
+    out = ops.umma_probe(at, b, 3, 64, k, idesc, 16384, 1024, 16384, 1024, 2048)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    rel = err / ref.abs().max().item()
+    return {"max_abs_err": err, "rel": rel, "ok": rel < 2e-2}
+
+
 def _ref_ring(qs, ks, vs, layout, causal, window, softclamp, key_masks):
     import torch
     from ring_attention_pytorch_b200.ops.oracle import attention_with_positions
@@ -360,6 +380,8 @@ CASES = {
     "ring3_kmask": lambda: case_fwd(world=3, n=200, h=2, kmask=True),
     "ring8_striped_causal_big": lambda: case_fwd(world=8, n=1024, h=8, hk=2, layout="striped", causal=True),
     # backward, single rank
+    "xprobe_mn_a": lambda: case_probe_mn_a(),
+    "xprobe_mn_a_k64": lambda: case_probe_mn_a(64),
     "bwd_d128_n256": lambda: case_bwd(),
     "bwd_d128_n128_h1": lambda: case_bwd(n=128, h=1),
     "bwd_d128_n64_h1": lambda: case_bwd(n=64, h=1),
