@@ -411,7 +411,8 @@ __device__ __forceinline__ void dq_issue_dq(DqSmem<D>& sm, const AttnBwdParams& 
   }
 }
 
-template <int D, bool BF16, bool TWO>
+// POLYQ of every 4 logit pairs take their exponential on the FMA pipe (poly_exp2x2, ptx.cuh) instead of the MUFU.
+template <int D, bool BF16, bool TWO, int POLYQ>
 __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem) {
   const int wg_tid = threadIdx.x - 128 * W;
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
@@ -506,8 +507,9 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
 #pragma unroll
         for (int j = 0; j < 128; j += 2) {
           const float2 a = ffma2(make_float2(__uint_as_float(sr[j]), __uint_as_float(sr[j + 1])), mul2, nl2);
-          sr[j] = __float_as_uint(fast_exp2(a.x));
-          sr[j + 1] = __float_as_uint(fast_exp2(a.y));
+          const float2 e = (((j >> 1) & 3) < POLYQ) ? poly_exp2x2(a) : make_float2(fast_exp2(a.x), fast_exp2(a.y));
+          sr[j] = __float_as_uint(e.x);
+          sr[j + 1] = __float_as_uint(e.y);
         }
       }
       mbar_wait(b_dp_full, bpar, 710 + W);
@@ -616,7 +618,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
   }
 }
 
-template <int D, bool BF16, bool TWO>
+template <int D, bool BF16, bool TWO, int POLYQ>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_constant__ CUtensorMap map_kv,
                    const __grid_constant__ AttnBwdParams p) {
@@ -669,7 +671,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_cons
     }
   } else {
     setmaxnreg_inc<192>();
-    dq_softmax<D, BF16, TWO>(sm, p, warp < 4 ? 0 : 1, tmem);
+    dq_softmax<D, BF16, TWO, POLYQ>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
   tc_fence_before();
   __syncthreads();
@@ -1142,7 +1144,7 @@ __device__ __forceinline__ void dkv_issue_acc(DkvSmem<D>& sm, const AttnBwdParam
   }
 }
 
-template <int D, bool BF16, bool PIPE>
+template <int D, bool BF16, bool PIPE, int POLYQ>
 __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem) {
   const int wg_tid = threadIdx.x - 128 * W;
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
@@ -1211,7 +1213,10 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
                                    make_float2(-lv.x, -lv.y));
           const float2 a23 = ffma2(make_float2(__uint_as_float(sr[q4 * 4 + 2]), __uint_as_float(sr[q4 * 4 + 3])), mul2,
                                    make_float2(-lv.z, -lv.w));
-          const float p0 = fast_exp2(a01.x), p1 = fast_exp2(a01.y), p2 = fast_exp2(a23.x), p3 = fast_exp2(a23.y);
+          const float2 e01 = (((2 * q4) & 3) < POLYQ) ? poly_exp2x2(a01) : make_float2(fast_exp2(a01.x), fast_exp2(a01.y));
+          const float2 e23 =
+              (((2 * q4 + 1) & 3) < POLYQ) ? poly_exp2x2(a23) : make_float2(fast_exp2(a23.x), fast_exp2(a23.y));
+          const float p0 = e01.x, p1 = e01.y, p2 = e23.x, p3 = e23.y;
           sr[q4 * 4 + 0] = __float_as_uint(p0);
           sr[q4 * 4 + 1] = __float_as_uint(p1);
           sr[q4 * 4 + 2] = __float_as_uint(p2);
@@ -1341,7 +1346,7 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
   }
 }
 
-template <int D, bool BF16, int MODE>
+template <int D, bool BF16, int MODE, int POLYQ>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_constant__ CUtensorMap map_kv,
                      const __grid_constant__ AttnBwdParams p) {
@@ -1387,7 +1392,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
     }
   } else {
     setmaxnreg_inc<192>();
-    dkv_softmax<D, BF16, (MODE != 0)>(sm, p, warp < 4 ? 0 : 1, tmem);
+    dkv_softmax<D, BF16, (MODE != 0), POLYQ>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
   tc_fence_before();
   __syncthreads();
@@ -1448,6 +1453,16 @@ __global__ void bwd_prep_kernel(const uint16_t* __restrict__ q, const uint16_t* 
 
 }  // namespace
 
+// RAB_BWD_EXP_POLY=1 (experimental, default 0): a quarter of the backward's P-recompute exponentials on the FMA pipe,
+// the switch that gave the forward +5 %; not yet timed for the backward.
+static bool bwd_exp_poly() {
+  static const bool on = [] {
+    const char* e = std::getenv("RAB_BWD_EXP_POLY");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
 template <int D>
 void launch_attn_bwd_dq(const CUtensorMap& map_qd, const CUtensorMap& map_kv, const AttnBwdParams& p, int num_sms,
                         cudaStream_t stream) {
@@ -1457,8 +1472,11 @@ void launch_attn_bwd_dq(const CUtensorMap& map_qd, const CUtensorMap& map_kv, co
     const char* e = std::getenv("RAB_DQ_TWO");
     return e == nullptr || e[0] != '0';
   }();
-  auto kern = two ? (p.is_bf16 ? attn_bwd_dq_kernel<D, true, true> : attn_bwd_dq_kernel<D, false, true>)
-                  : (p.is_bf16 ? attn_bwd_dq_kernel<D, true, false> : attn_bwd_dq_kernel<D, false, false>);
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const AttnBwdParams);
+  Kern kern;
+  if (!two) kern = p.is_bf16 ? attn_bwd_dq_kernel<D, true, false, 0> : attn_bwd_dq_kernel<D, false, false, 0>;
+  else if (bwd_exp_poly()) kern = p.is_bf16 ? attn_bwd_dq_kernel<D, true, true, 1> : attn_bwd_dq_kernel<D, false, true, 1>;
+  else kern = p.is_bf16 ? attn_bwd_dq_kernel<D, true, true, 0> : attn_bwd_dq_kernel<D, false, true, 0>;
   const size_t smem = sizeof(DqSmem<D>) + 1024;
   cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "bwd_dq smem attr");
   const int items = p.batch * p.heads * ((p.n_q + 127) / 128);
@@ -1478,9 +1496,11 @@ void launch_attn_bwd_dkdv(const CUtensorMap& map_qd64, const CUtensorMap& map_kv
   }();
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const AttnBwdParams);
   Kern kern;
-  if (mode == 2) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 2> : attn_bwd_dkdv_kernel<D, false, 2>;
-  else if (mode == 1) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 1> : attn_bwd_dkdv_kernel<D, false, 1>;
-  else kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 0> : attn_bwd_dkdv_kernel<D, false, 0>;
+  if (mode == 2 && bwd_exp_poly())
+    kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 2, 1> : attn_bwd_dkdv_kernel<D, false, 2, 1>;
+  else if (mode == 2) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 2, 0> : attn_bwd_dkdv_kernel<D, false, 2, 0>;
+  else if (mode == 1) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 1, 0> : attn_bwd_dkdv_kernel<D, false, 1, 0>;
+  else kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 0, 0> : attn_bwd_dkdv_kernel<D, false, 0, 0>;
   const size_t smem = sizeof(DkvSmem<D>) + 1024;
   cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
              "bwd_dkdv smem attr");
