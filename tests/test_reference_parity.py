@@ -171,3 +171,23 @@ def test_ring_transformer_forward_matches_reference_under_gloo(ref, striped):
     from dist_utils import run_distributed
 
     run_distributed(_ring_transformer_parity_worker, 2, striped)
+
+
+def _tree_parity_worker(rank, world, seq_len):
+    sys.path.insert(0, REF)
+    import ring_attention_pytorch as theirs
+
+    from ring_attention_pytorch_b200 import tree_attn_decode
+
+    torch.manual_seed(0)  # identical inputs on every rank; both implementations shard K/V by rank internally
+    q, k, v = torch.randn(2, 4, 1, 8), torch.randn(2, 4, seq_len, 8), torch.randn(2, 4, seq_len, 8)
+    want = theirs.tree_attn_decode(q, k, v, use_triton=False)
+    assert torch.allclose(tree_attn_decode(q, k, v), want, atol=1e-5)
+
+
+@pytest.mark.parametrize("seq_len", [2, 31])  # 2 < world: some ranks hold no keys at all
+def test_tree_decode_matches_reference_under_gloo(ref, seq_len):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dist_utils import run_distributed
+
+    run_distributed(_tree_parity_worker, 3, seq_len)
