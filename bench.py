@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--dim-head", type=int, default=128)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--probe-device", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--fwd-only", action="store_true", help="diagnostic only (not a valid headline number)")
     return ap.parse_args()
 
@@ -122,8 +123,58 @@ def install_reference_shims():
     sys.path.insert(0, ref)
 
 
+def probe_reference_backward(local_rank: int) -> dict:
+    """Does the reference's stock backward launch on this GPU?  Asked in a SUBPROCESS (tiny problem, one device) so that a
+    kernel that compiles but cannot be loaded does not stay in this process's Triton cache.
+
+    On sm_100, Triton 3.6 lowers the reference's 128x128 ``_bwd_kernel`` to tcgen05 with 704 TMEM columns (512 exist) and
+    the launch raises OutOfResources.  Triton has its own switch for that, ``DISABLE_MMA_V5`` (emit mma.sync); when the
+    probe reports exactly that failure the reference arm sets it AFTER its forward kernels were compiled (they keep
+    tcgen05) and BEFORE its first backward.  The reference's code and call path are untouched, and the switch is reported
+    in the JSON line.  Any other outcome leaves the environment alone."""
+    if "DISABLE_MMA_V5" in os.environ:
+        return {}
+    try:
+        env = {k_: v_ for k_, v_ in os.environ.items()
+               if k_ not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK")}
+        proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--probe-device",
+                               str(local_rank)], capture_output=True, text=True, timeout=600, env=env)
+        lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+        res = json.loads(lines[-1]) if lines else {}
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] reference probe did not run: {type(e).__name__}: {e}", file=sys.stderr)
+        return {}
+    err = res.get("probe_error", "")
+    if "tensor memory" in err:
+        return {"DISABLE_MMA_V5": "1 (set between the first forward and the first backward)", "because": err[:200]}
+    return {}
+
+
+def run_reference_probe(device_index: int) -> None:
+    """Body of the probe subprocess: one tiny forward + backward of the reference on one GPU, stock environment."""
+    import torch
+
+    res = {}
+    try:
+        torch.cuda.set_device(device_index)
+        install_reference_shims()
+        from ring_attention_pytorch.ring_flash_attention_cuda import ring_flash_attn_cuda as ref_attn
+
+        q, k, v = (torch.randn(1, 1024, 2, 128, device="cuda", dtype=torch.bfloat16, requires_grad=True) for _ in range(3))
+        out = ref_attn(q, k, v, None, True, 1024, False, False, None, 1)
+        out.backward(torch.randn_like(out))
+        torch.cuda.synchronize()
+        res["probe_ok"] = True
+    except BaseException as e:  # noqa: BLE001
+        res["probe_error"] = f"{type(e).__name__}: {e}".replace("\n", " ")[:400]
+    print(json.dumps(res))
+
+
 def main():
     args = parse_args()
+    if args.probe_device is not None:
+        run_reference_probe(args.probe_device)
+        return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -168,6 +219,7 @@ def main():
             return ref_attn(q, k, v, None, True, min(n, 1024), ring, ring, None, world)
 
         launches = {"count": 0}
+        ref_env = probe_reference_backward(local_rank)
     else:
         from ring_attention_pytorch_b200.ops import ring_cuda
 
@@ -175,6 +227,7 @@ def main():
             return ring_cuda.ring_flash_attn_cuda(q, k, v, None, True, 1024, ring, ring, None, world)
 
         launches = ring_cuda.LAUNCHES
+        ref_env = {}
 
     torch.manual_seed(1234 + rank)
     dt = torch.bfloat16
@@ -187,6 +240,8 @@ def main():
         out = attn(q, k, v)
         if args.fwd_only:
             return out
+        if ref_env:
+            os.environ["DISABLE_MMA_V5"] = "1"  # forward kernels are compiled by now and keep tcgen05
         out.backward(w)
         q.grad = k.grad = v.grad = None
         return out
@@ -337,6 +392,7 @@ def main():
                 "flops": "fwd 4*b*h*S^2*d*0.5, bwd 2.5x fwd (algorithmic 5-GEMM count)",
                 "l2": "inputs larger than L2 (no flush needed)",
                 "fwd_only": bool(args.fwd_only),
+                **({"reference_env": ref_env} if ref_env else {}),
             },
             "clocks": clocks,
             "e2e": e2e,
