@@ -698,8 +698,15 @@ struct DkvSmem {
   uint64_t qd_full[QSTAGES], qd_empty[QSTAGES];
   uint64_t sdp_full[2], pds_ready[2];
   uint64_t s_full[2], s_free[2], dp_full[2];  // pipelined variant
+  uint64_t dq_full[2], x_free[2];             // one-kernel variant (MODE 3)
   uint64_t acc_done, epi_done;
   uint32_t tmem_base;
+};
+
+// MODE 3 adds one [128 keys x 64 queries] 16-bit tile per stream: dS^T as the B operand of dQ^T = K^T dS^T
+template <int D>
+struct DkvFusedSmem : DkvSmem<D> {
+  alignas(1024) uint8_t ds[2][128 * 128];
 };
 
 struct DkvItem {
@@ -1019,7 +1026,7 @@ __device__ __forceinline__ void dkv_mma_pipe(DkvSmem<D>& sm, const AttnBwdParams
 //   warp 10 "acc issuer" : dP^T(j) into Y_w, dV/dK(j) from Y_w   gated by qd_full(stage j), pds_ready[w]
 // The two warps never touch the same TMEM block, and only warp 10 accumulates into dK/dV, so no cross-warp ordering of
 // tcgen05.mma is relied upon.
-template <int D, bool BF16>
+template <int D, bool BF16, bool FUSED>
 __device__ __forceinline__ void dkv_issue_s(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);
   constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
@@ -1044,7 +1051,9 @@ __device__ __forceinline__ void dkv_issue_s(DkvSmem<D>& sm, const AttnBwdParams&
       const uint32_t g = tile_base + j;
       const uint32_t st = g % QSTAGES, ph = (g / QSTAGES) & 1;
       mbar_wait(&sm.qd_full[st], ph, 920 + st);
-      if (c_s[w] > 0) mbar_wait(&sm.s_free[w], (c_s[w] - 1u) & 1, 930 + w);
+      // X_w is free once S^T has been pulled into registers — or, in the one-kernel variant, once dQ^T (which reuses
+      // the block) has been drained to global memory
+      if (c_s[w] > 0) mbar_wait(FUSED ? &sm.x_free[w] : &sm.s_free[w], (c_s[w] - 1u) & 1, 930 + w);
       tc_fence_after();
       const uint32_t x_tm = tmem + w * 128u;
       const uint64_t qk = q_kdesc0 + uint64_t(st * STAGE16);
@@ -1065,8 +1074,9 @@ __device__ __forceinline__ void dkv_issue_s(DkvSmem<D>& sm, const AttnBwdParams&
   }
 }
 
-template <int D, bool BF16>
-__device__ __forceinline__ void dkv_issue_acc(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
+template <int D, bool BF16, bool FUSED>
+__device__ __forceinline__ void dkv_issue_acc(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in,
+                                              uint32_t ds_smem_base) {
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);
   constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);
   constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
@@ -1132,6 +1142,20 @@ __device__ __forceinline__ void dkv_issue_acc(DkvSmem<D>& sm, const AttnBwdParam
           umma_ts(dk_tm, y_tm + 32 + kk * 8, umma_desc_add(qmn, kk * 2048), idesc_acc, kk > 0 ? 1u : acc0);
         }
         umma_commit(&sm.qd_empty[st]);
+        if constexpr (FUSED) {
+          // dQ^T[d, q] = K^T[d, keys] dS^T[keys, q]: A = the K tile read MN-major (like V in the forward's P V),
+          // B = the dS^T tile the warpgroup wrote to shared memory; D reuses X_w (S^T is long in registers)
+          constexpr uint32_t idesc_dqt = umma_idesc_bf16(D, 64, 1, 1, BF16 ? 1 : 0);
+          constexpr uint64_t mn_static = umma_smem_desc_hi_lo(SUB128, 1024, UMMA_LAYOUT_SW128);
+          const uint64_t k_mn = umma_desc(mn_static, smem_u32(sm.k));
+          const uint64_t ds_mn = umma_desc(mn_static, ds_smem_base + w * (128 * 128));
+          const uint32_t x_tm = tmem + w * 128u;
+#pragma unroll
+          for (int kk = 0; kk < 128 / 16; ++kk) {
+            umma_ss(x_tm, umma_desc_add(k_mn, kk * 2048), umma_desc_add(ds_mn, kk * 2048), idesc_dqt, kk > 0);
+          }
+          umma_commit(&sm.dq_full[w]);
+        }
       }
       __syncwarp();
       c_b[w]++;
@@ -1144,8 +1168,9 @@ __device__ __forceinline__ void dkv_issue_acc(DkvSmem<D>& sm, const AttnBwdParam
   }
 }
 
-template <int D, bool BF16, bool PIPE, int POLYQ>
-__device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem) {
+template <int D, bool BF16, bool PIPE, int POLYQ, bool FUSED>
+__device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem,
+                                            uint8_t* ds_smem) {
   const int wg_tid = threadIdx.x - 128 * W;
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
   const uint32_t st_tm = tmem + W * 128 + lane_off;
@@ -1186,7 +1211,7 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
         tmem_ld32(st_tm + 32, sr + 32);
         tc_wait_ld();
         tc_fence_before();
-        mbar_arrive((&sm.s_free[0] + W));  // X_w may take S^T of this stream's next tile now
+        if constexpr (!FUSED) mbar_arrive((&sm.s_free[0] + W));  // X_w may take S^T of this stream's next tile now
       } else {
         mbar_wait((&sm.sdp_full[0] + W), cnt & 1, 1000 + W);
         tc_fence_after();
@@ -1301,9 +1326,41 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
         tmem_st32(st_tm, pw);
         tmem_st32(dpt_tm, dw);
       }
+      if constexpr (FUSED) {
+        // dS^T row of this key into shared memory, 128B swizzle applied by hand (chunk c of row r sits at c ^ (r % 8))
+        uint8_t* row = ds_smem + W * (128 * 128) + wg_tid * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(row + ((c ^ (wg_tid & 7)) << 4)) =
+              make_uint4(dw[4 * c], dw[4 * c + 1], dw[4 * c + 2], dw[4 * c + 3]);
+        fence_proxy_async_shared();
+      }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive((&sm.pds_ready[0] + W));
+      if constexpr (FUSED) {
+        // drain dQ^T (lane = d index, 64 query columns) into the fp32 accumulator: for a fixed query row the 32 lanes
+        // of a warp hit 32 consecutive floats
+        mbar_wait((&sm.dq_full[0] + W), cnt & 1, 1008 + W);
+        tc_fence_after();
+        uint32_t g0[32], g1[32];
+        tmem_ld32(st_tm + 0, g0);
+        tmem_ld32(st_tm + 32, g1);
+        tc_wait_ld();
+        tc_fence_before();
+        mbar_arrive((&sm.x_free[0] + W));
+        const int head = t.rep * p.kv_heads + it.kvh;
+        const int q0 = t.idx * 64;
+        float* base = p.dq_acc + (((size_t)it.b * p.n_q + q0) * p.heads + head) * D + wg_tid;
+        const size_t row_stride = (size_t)p.heads * D;
+        const int nrow = min(64, p.n_q - q0);
+#pragma unroll
+        for (int qq = 0; qq < 32; ++qq)
+          if (qq < nrow) red_add_f32(base + qq * row_stride, __uint_as_float(g0[qq]) * p.scale);
+#pragma unroll
+        for (int qq = 0; qq < 32; ++qq)
+          if (qq + 32 < nrow) red_add_f32(base + (qq + 32) * row_stride, __uint_as_float(g1[qq]) * p.scale);
+      }
       cnt++;
     }
     tile_base += jn;  // both warpgroups walk the whole sequence, so the stage ring stays in step
@@ -1351,11 +1408,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_constant__ CUtensorMap map_kv,
                      const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  DkvSmem<D>& sm = *reinterpret_cast<DkvSmem<D>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr bool FUSED = MODE == 3;  // two issuers + dQ^T in the same kernel (experimental)
+  constexpr bool TWO_ISSUERS = MODE >= 2;
+  DkvFusedSmem<D>& fsm =
+      *reinterpret_cast<DkvFusedSmem<D>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  DkvSmem<D>& sm = fsm;  // the dS^T tiles behind it are only touched (and only allocated) when FUSED
   const int warp = threadIdx.x / 32;
   if (threadIdx.x == 0) {
     mbar_init(&sm.kv_full, 1);
-    mbar_init(&sm.kv_empty, MODE == 2 ? 2 : 1);
+    mbar_init(&sm.kv_empty, TWO_ISSUERS ? 2 : 1);
     for (int i = 0; i < QSTAGES; ++i) {
       mbar_init(&sm.qd_full[i], 1);
       mbar_init(&sm.qd_empty[i], 1);
@@ -1366,6 +1427,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
       mbar_init(&sm.s_full[i], 1);
       mbar_init(&sm.s_free[i], 128);
       mbar_init(&sm.dp_full[i], 1);
+      mbar_init(&sm.dq_full[i], 1);
+      mbar_init(&sm.x_free[i], 128);
     }
     mbar_init(&sm.acc_done, 1);
     mbar_init(&sm.epi_done, 256);
@@ -1383,16 +1446,16 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
     setmaxnreg_dec<120>();
     if (warp == 8) dkv_producer<D>(sm, p, &map_qd64, &map_kv);
     if (warp == 9) {
-      if constexpr (MODE == 2) dkv_issue_s<D, BF16>(sm, p, tmem);
+      if constexpr (TWO_ISSUERS) dkv_issue_s<D, BF16, FUSED>(sm, p, tmem);
       else if constexpr (MODE == 1) dkv_mma_pipe<D, BF16>(sm, p, tmem);
       else dkv_mma<D, BF16>(sm, p, tmem);
     }
     if (warp == 10) {
-      if constexpr (MODE == 2) dkv_issue_acc<D, BF16>(sm, p, tmem);
+      if constexpr (TWO_ISSUERS) dkv_issue_acc<D, BF16, FUSED>(sm, p, tmem, FUSED ? smem_u32(fsm.ds[0]) : 0u);
     }
   } else {
     setmaxnreg_inc<192>();
-    dkv_softmax<D, BF16, (MODE != 0), POLYQ>(sm, p, warp < 4 ? 0 : 1, tmem);
+    dkv_softmax<D, BF16, (MODE != 0), POLYQ, FUSED>(sm, p, warp < 4 ? 0 : 1, tmem, FUSED ? fsm.ds[0] : nullptr);
   }
   tc_fence_before();
   __syncthreads();
@@ -1496,12 +1559,16 @@ void launch_attn_bwd_dkdv(const CUtensorMap& map_qd64, const CUtensorMap& map_kv
   }();
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const AttnBwdParams);
   Kern kern;
-  if (mode == 2 && bwd_exp_poly())
+  bool fused = false;
+  if constexpr (D == 128) fused = p.dq_acc != nullptr;
+  if (fused) {
+    if constexpr (D == 128) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<128, true, 3, 0> : attn_bwd_dkdv_kernel<128, false, 3, 0>;
+  } else if (mode == 2 && bwd_exp_poly())
     kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 2, 1> : attn_bwd_dkdv_kernel<D, false, 2, 1>;
   else if (mode == 2) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 2, 0> : attn_bwd_dkdv_kernel<D, false, 2, 0>;
   else if (mode == 1) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 1, 0> : attn_bwd_dkdv_kernel<D, false, 1, 0>;
   else kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 0, 0> : attn_bwd_dkdv_kernel<D, false, 0, 0>;
-  const size_t smem = sizeof(DkvSmem<D>) + 1024;
+  const size_t smem = (fused ? sizeof(DkvFusedSmem<D>) : sizeof(DkvSmem<D>)) + 1024;
   cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
              "bwd_dkdv smem attr");
   const int items = p.batch * p.kv_heads * ((p.n_k + 127) / 128);

@@ -302,6 +302,36 @@ std::tuple<Tensor, Tensor> attn_bwd_dkdv(const Tensor& qdo_buf, const Tensor& kv
   return {dk, dv};
 }
 
+// Experimental one-kernel backward (single rank, D = 128): dK/dV as above, dQ accumulated into `dq_acc` (fp32
+// [b, n_q, h, d], zero-initialised by the caller) with red.global.add.f32.  See attn_bwd_sm100.cu, MODE 3.
+std::tuple<Tensor, Tensor> attn_bwd_fused(const Tensor& qdo_buf, const Tensor& kv_buf, const Tensor& stat_buf,
+                                         const c10::optional<Tensor>& ready, int64_t ready_target,
+                                         const c10::optional<Tensor>& kmask_bits, int64_t batch, int64_t heads,
+                                         int64_t kv_heads, int64_t rank, bool causal, int64_t window, double scale,
+                                         double softclamp, int64_t pos_stride, int64_t seg_len, at::IntArrayRef base0,
+                                         at::IntArrayRef base1, int64_t q_pos_offset, at::IntArrayRef hop_owner, Tensor dq_acc) {
+  c10::cuda::CUDAGuard guard(kv_buf.device());
+  BwdSetup s = make_bwd_setup(qdo_buf, kv_buf, stat_buf, ready, ready_target, kmask_bits, batch, heads, kv_heads, rank,
+                              causal, window, scale, softclamp, pos_stride, seg_len, base0, base1, q_pos_offset,
+                              hop_owner);
+  const int d = kv_buf.size(4);
+  TORCH_CHECK(d == 128 && hop_owner.size() == 1, "attn_bwd_fused: head dim 128, single rank only");
+  TORCH_CHECK(dq_acc.scalar_type() == at::kFloat && dq_acc.is_contiguous() && dq_acc.is_cuda());
+  TORCH_CHECK(dq_acc.numel() == (int64_t)batch * s.p.n_q * heads * d, "dq_acc must be [b, n_q, h, d] fp32");
+  s.p.dq_acc = dq_acc.data_ptr<float>();
+  Tensor dk = torch::empty({batch, s.p.n_k, kv_heads, d}, kv_buf.options());
+  Tensor dv = torch::empty({batch, s.p.n_k, kv_heads, d}, kv_buf.options());
+  s.p.dk = dk.data_ptr();
+  s.p.dv = dv.data_ptr();
+  auto stream = at::cuda::getCurrentCUDAStream();
+  if (d == 128) {
+    rab::launch_attn_bwd_dkdv<128>(s.map_qd64, s.map_kv, s.p, sm_count(), stream);
+  } else {
+    rab::launch_attn_bwd_dkdv<64>(s.map_qd64, s.map_kv, s.p, sm_count(), stream);
+  }
+  return {dk, dv};
+}
+
 // ---------------------------------------------------------------------------------------------
 // tree-attention decode
 // ---------------------------------------------------------------------------------------------
@@ -446,6 +476,10 @@ TORCH_LIBRARY(rab, m) {
         "kmask_bits, int batch, int heads, int kv_heads, int rank, bool causal, int window, float scale, float "
         "softclamp, int pos_stride, int seg_len, int[] base0, int[] base1, int q_pos_offset, int[] hop_owner) -> "
         "(Tensor, Tensor)");
+  m.def("attn_bwd_fused(Tensor qdo_buf, Tensor kv_buf, Tensor stat_buf, Tensor? ready, int ready_target, Tensor? "
+        "kmask_bits, int batch, int heads, int kv_heads, int rank, bool causal, int window, float scale, float "
+        "softclamp, int pos_stride, int seg_len, int[] base0, int[] base1, int q_pos_offset, int[] hop_owner, Tensor(a!) dq_acc) -> "
+        "(Tensor, Tensor)");
   m.def("device_barrier(int[] pad_ptrs, int rank, int epoch) -> ()");
   m.def("peer_copy(Tensor(a!) dst, int src_ptr, int nbytes) -> ()");
   m.def("symm_alloc(int bytes) -> (Tensor, Tensor)");
@@ -461,6 +495,7 @@ TORCH_LIBRARY_IMPL(rab, CUDA, m) {
   m.impl("bwd_prep", &bwd_prep);
   m.impl("attn_bwd_dq", &attn_bwd_dq);
   m.impl("attn_bwd_dkdv", &attn_bwd_dkdv);
+  m.impl("attn_bwd_fused", &attn_bwd_fused);
 }
 
 TORCH_LIBRARY_IMPL(rab, CompositeExplicitAutograd, m) {

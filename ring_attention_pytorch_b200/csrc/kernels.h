@@ -105,6 +105,7 @@ struct AttnBwdParams {
   int kmask_words;
   const uint32_t* ready;       // [world] flags: slot o usable once ready[o] >= ready_target (may be null)
   uint32_t ready_target;
+  float* dq_acc;               // experimental one-kernel backward: fp32 [b, n_q, h, d] accumulator (null = off)
 };
 
 template <int D>

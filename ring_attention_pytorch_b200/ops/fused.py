@@ -142,6 +142,35 @@ def fused_attn_bwd(
     return dq, dk, dv
 
 
+def fused_attn_bwd_one_kernel(
+    qdo_buf: torch.Tensor,
+    kv_buf: torch.Tensor,
+    stat_buf: torch.Tensor,
+    kmask_bits: Optional[torch.Tensor],
+    *,
+    batch: int,
+    heads: int,
+    kv_heads: int,
+    n_q: int,
+    pm: PositionMap,
+    causal: bool,
+    window: Optional[int],
+    scale: float,
+    softclamp: float = 0.0,
+    q_pos_offset: int = 0,
+):
+    """EXPERIMENTAL (compile-checked, not yet validated on a GPU): the whole backward in the KV-stationary kernel — S and
+    dP are computed once (5 GEMMs instead of 7), dQ^T = K^T dS^T is reduced into an fp32 accumulator with
+    ``red.global.add.f32``.  Single rank, head dim 128 only.  Returns (dq fp32 [b, n_q, h, d], dk, dv)."""
+    ops = _ext.ops()
+    d = kv_buf.shape[-1]
+    dq_acc = torch.zeros(batch, n_q, heads, d, dtype=torch.float32, device=kv_buf.device)
+    dk, dv = ops.attn_bwd_fused(qdo_buf, kv_buf, stat_buf, None, 0, kmask_bits, batch, heads, kv_heads, 0, bool(causal),
+                                int(window or 0), float(scale), float(softclamp), pm.stride, pm.seg_len, pm.base0,
+                                pm.base1, int(q_pos_offset), [0], dq_acc)
+    return dq_acc, dk, dv
+
+
 def emulate_ring_backward(
     qs, ks, vs, outs, lses, douts, *,
     layout: str = "plain",

@@ -44,7 +44,9 @@ LAUNCHES = {"count": 0}
 # save_kv_gather=False: only this rank's K/V slot is kept (O(n) activation memory per layer, the classic ring
 #                       attention footprint); the backward re-pulls the peers' slots with the copy engines before
 #                       the dQ kernel starts.
-CONFIG = {"save_kv_gather": True}
+# fused_backward=True  : EXPERIMENTAL, not yet validated on a GPU — single-rank, head-dim-128 calls run the whole
+#                        backward in one KV-stationary kernel (5 GEMMs, dQ through fp32 global reductions).
+CONFIG = {"save_kv_gather": True, "fused_backward": False}
 
 
 def _count(n: int = 1) -> None:
@@ -205,6 +207,19 @@ class RingFlashAttentionCUDAFunction(Function):
                 gather_done.record(ws.side_stream)
             qdo_gather.record_stream(ws.side_stream)
             stat_gather.record_stream(ws.side_stream)
+
+        if CONFIG["fused_backward"] and not use_ring and d_pad == 128:
+            from ring_attention_pytorch_b200.ops.fused import fused_attn_bwd_one_kernel
+
+            dq32, dk, dv = fused_attn_bwd_one_kernel(qdo_gather, kv_gather, stat_gather, kbits, batch=b, heads=h,
+                                                     kv_heads=hk, n_q=n_q, pm=pm, causal=causal, window=window,
+                                                     scale=scale, softclamp=softclamp, q_pos_offset=q_off)
+            _count(1)
+            dq = dq32.to(dt)
+            dq, dk, dv = dq[..., :d], dk[..., :d], dv[..., :d]
+            if orig_dtype != dt:
+                dq, dk, dv = dq.to(orig_dtype), dk.to(orig_dtype), dv.to(orig_dtype)
+            return dq, dk, dv, None, None, None, None, None, None, None, None, None, None
 
         common = (kbits, b, h, hk, rank, bool(causal), int(window or 0), float(scale), float(softclamp), pm.stride,
                   pm.seg_len, pm.base0, pm.base1, int(q_off))

@@ -76,6 +76,34 @@ def case_probe_mn_a(k: int = 128):
     return {"max_abs_err": err, "rel": rel, "ok": rel < 2e-2}
 
 
+def case_fused_bwd(causal=True, n=1024, h=4, hk=4, b=2):
+    """Not validated yet: the experimental one-kernel backward (CONFIG['fused_backward']) against the two-kernel one and
+    the fp32 oracle, plus timings of both."""
+    import torch
+    from ring_attention_pytorch_b200.ops import ring_cuda
+    from ring_attention_pytorch_b200.ops.oracle import default_attention
+
+    torch.manual_seed(0)
+    q, k, v = (torch.randn(b, n, hh, 128, device="cuda", dtype=torch.bfloat16, requires_grad=True) for hh in (h, hk, hk))
+    g = torch.randn(b, n, h, 128, device="cuda", dtype=torch.bfloat16)
+    res = {}
+    grads = {}
+    for name, flag in (("two_kernel", False), ("one_kernel", True)):
+        ring_cuda.CONFIG["fused_backward"] = flag
+        out = ring_cuda.ring_flash_attn_cuda(q, k, v, None, causal)
+        grads[name] = torch.autograd.grad(out, (q, k, v), g)
+    ring_cuda.CONFIG["fused_backward"] = False
+    qf, kf, vf = (t.detach().float().requires_grad_() for t in (q, k, v))
+    want = torch.autograd.grad(default_attention(qf, kf, vf, causal=causal), (qf, kf, vf), g.float())
+    ok = True
+    for name in grads:
+        rel = [((a.float() - w).abs().max() / w.abs().max()).item() for a, w in zip(grads[name], want)]
+        res[name] = rel
+        ok = ok and all(r < 3e-2 for r in rel)
+    res["ok"] = ok
+    return res
+
+
 def _ref_ring(qs, ks, vs, layout, causal, window, softclamp, key_masks):
     import torch
     from ring_attention_pytorch_b200.ops.oracle import attention_with_positions
@@ -380,6 +408,8 @@ CASES = {
     "ring3_kmask": lambda: case_fwd(world=3, n=200, h=2, kmask=True),
     "ring8_striped_causal_big": lambda: case_fwd(world=8, n=1024, h=8, hk=2, layout="striped", causal=True),
     # backward, single rank
+    "xfused_bwd_causal": lambda: case_fused_bwd(causal=True),
+    "xfused_bwd_full_gqa": lambda: case_fused_bwd(causal=False, hk=2, n=700),
     "xprobe_mn_a": lambda: case_probe_mn_a(),
     "xprobe_mn_a_k64": lambda: case_probe_mn_a(64),
     "bwd_d128_n256": lambda: case_bwd(),

@@ -16,6 +16,8 @@ run timeout 60 python tools/gpu_dev_check.py --timeout 40 --only perf_causal_16k
 # 3. FMA-pipe exponentials in the backward
 RAB_BWD_EXP_POLY=1 run timeout 120 python tools/gpu_dev_check.py --timeout 40 \
     --only bwd_d128_causal_n1000,bwd_many_items,bwd_d64_causal_n777,perfbwd_causal_16k,perfbwd_causal_64k_h8
+# 3b. experimental one-kernel backward (needs step 1 green: it relies on the probe-mode-3 operand flavours)
+run timeout 120 python tools/gpu_dev_check.py --timeout 50 --only xfused_bwd_causal,xfused_bwd_full_gqa
 # 4. bench with the prefetching e2e loop, then the reference arm with its probe
 run timeout 240 python bench.py --steps 3 --warmup 3
 run timeout 600 python bench.py --impl reference --steps 2 --warmup 3
