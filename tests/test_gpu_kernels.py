@@ -431,3 +431,17 @@ def test_hop_api_kernel_path_matches_dense_path(d):
         assert (dl_k - dl_d).abs().max() < 5e-2
         for a, w in zip(got, want):
             assert (a.float() - w).abs().max() / w.abs().max() < 4e-2, (i, kw.keys())
+
+
+def test_tcgen05_issue_rate_matches_hardware_floor():
+    """The calibration behind the tile-time models in BASELINE.md (tools/mma_rate.py): with a tight, unrolled issue loop a
+    128x128x16 tcgen05.mma costs 64 cycles (SS and TS), the N=64 TS form 32 and the N=64 SS form 48 (smem-operand bound)."""
+    from ring_attention_pytorch_b200.ops import _ext
+
+    ops = _ext.ops()
+    reps = 2048
+    expect = {(0, 128): 64.0, (2, 128): 64.0, (2, 64): 32.0, (0, 64): 48.0, (0, 256): 128.0}
+    for (mode, n), cyc in expect.items():
+        ops.umma_rate(mode, n, 256, 0, 2)  # warm-up
+        got = ops.umma_rate(mode, n, reps, 0, 4)[:, 0].float().mean().item() / reps
+        assert abs(got - cyc) / cyc < 0.08, (mode, n, got)
