@@ -30,6 +30,7 @@ CU_SOURCES = [
     "umma_probe.cu",
     "attn_fwd_sm100.cu",
     "attn_bwd_sm100.cu",
+    "attn_bwd_fused_sm100.cu",
     "tree_decode_sm100.cu",
     "elementwise_sm100.cu",
 ]

@@ -13,9 +13,11 @@
 // Triton kernel per hop but ships K, V, dK, dV around the ring in 16 bit, adds one extra dK/dV hop per
 // iteration and accumulates dQ through global read-modify-write.
 //
-// Both kernels run two independent "streams" (even / odd streamed tiles), each owning a TMEM region and a
-// 128-thread warpgroup; one MMA-issuing thread polls the two streams and issues whichever tcgen05.mma has
-// its dependencies satisfied, so a stream waiting on its warpgroup never blocks the tensor core.
+// Both kernels run two independent "streams" (even / odd streamed tiles), each owning TMEM blocks and a 128-thread
+// warpgroup, and two MMA-issuing warps whose waits are blocking in-order mbarrier waits.
+//
+// This pair is the backward of head dim 64 and the deterministic alternative at head dim 128, where the default is
+// the one-kernel, 5-GEMM backward in attn_bwd_fused_sm100.cu.
 //
 // Inputs are the *gathered* ring buffers (see kernels.h); remote slots are published through ready flags.
 #include "attn_common.cuh"
@@ -50,8 +52,7 @@ struct DqSmem {
   uint64_t qdo_full, qdo_empty;
   uint64_t k_full[3], k_empty[3];
   uint64_t v_full[2], v_empty[2];
-  uint64_t s_full[2], s_taken[2], dp_full[2], ds_ready[2];
-  uint64_t r_s_full[3], r_s_taken[3], r_dp_full[3], r_ds_ready[3], r_free[3];  // two-issuer variant: per TMEM region
+  uint64_t r_s_full[3], r_s_taken[3], r_dp_full[3], r_ds_ready[3], r_free[3];  // per TMEM region
   uint64_t dq_done, epi_done;
   uint32_t tmem_base;
 };
@@ -95,53 +96,6 @@ __device__ __forceinline__ void dq_init_scan(DqScan& sc, const AttnBwdParams& p,
   sc.mc = MaskCfg{p.causal, p.window, p.kmask_bits != nullptr};
   sc.st[0] = StatRange{it.qlo, it.qhi, true, false};
 }
-
-// lane 0 probes the barrier, the result is broadcast so the whole warp stays convergent
-__device__ __forceinline__ bool warp_test(uint64_t* bar, uint32_t parity, int lane) {
-  uint32_t ok = 0;
-  if (lane == 0) ok = mbar_test_wait(bar, parity) ? 1u : 0u;
-  return __shfl_sync(0xffffffffu, ok, 0) != 0;
-}
-
-// Hands the tiles of one scanner out to two streams alternately (tile j -> stream j & 1) while pulling from
-// the scanner strictly in order.  A stream may run at most one tile ahead of the other.
-template <class Scan>
-struct StreamFeeder {
-  Scan scan;
-  uint32_t seq = 0;
-  bool done = false;
-  ScanTile pend[2];
-  uint32_t pend_j[2];
-  bool pend_valid[2] = {false, false};
-  // returns 1: got a tile, 0: must wait for the other stream, -1: sequence exhausted for this stream
-  __device__ __forceinline__ int fetch(int w, int lane, ScanTile& out, uint32_t& j_out) {
-    if (pend_valid[w]) {
-      out = pend[w];
-      j_out = pend_j[w];
-      pend_valid[w] = false;
-      return 1;
-    }
-    while (!done) {
-      const int par = seq & 1;
-      if (par != w && pend_valid[par]) return 0;
-      ScanTile t;
-      if (!scan.next(lane, t)) {
-        done = true;
-        break;
-      }
-      const uint32_t j = seq++;
-      if (par == w) {
-        out = t;
-        j_out = j;
-        return 1;
-      }
-      pend[par] = t;
-      pend_j[par] = j;
-      pend_valid[par] = true;
-    }
-    return -1;
-  }
-};
 
 template <int D>
 __device__ __forceinline__ void dq_producer(DqSmem<D>& sm, const AttnBwdParams& p, const CUtensorMap* map_qd,
@@ -192,110 +146,8 @@ __device__ __forceinline__ void dq_producer(DqSmem<D>& sm, const AttnBwdParams& 
   }
 }
 
-template <int D, bool BF16>
-__device__ __forceinline__ void dq_mma(DqSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0, BF16 ? 1 : 0);   // S, dP : N = 128 keys
-  constexpr uint32_t idesc_dq = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);    // dQ    : N = D, B MN-major
-  constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
-  constexpr uint64_t mnmaj = umma_smem_desc_hi_lo(SUB128, 1024, UMMA_LAYOUT_SW128);
-  // whole warp in lock step with warp-uniform operands; the *_w wrappers elect the issuing lane
-  const int lane = lane_id();
-  const uint32_t tmem = warp_uniform(tmem_in);
-  const uint32_t x_tm[2] = {tmem + 0, tmem + 128};
-  const uint32_t dq_tm = tmem + 256;
-
-  uint32_t n_item = 0, tile_base = 0;
-  uint32_t cnt[2] = {0, 0};  // tiles completed per stream (global) -> barrier parities
-  const int total = dq_num_items(p);
-  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
-    DqItem it;
-    dq_decode(p, idx, it);
-    mbar_wait(&sm.qdo_full, n_item & 1, 600);
-    tc_fence_after();
-
-    StreamFeeder<DqScan> feed;
-    dq_init_scan(feed.scan, p, it);
-    ScanTile tl[2];
-    int state[2] = {-1, -1};  // -1: need a tile, 0: need S, 1: need dP, 2: need dQ, 3: done
-    uint32_t jj[2] = {0, 0};
-    bool dq_started = false;
-    uint32_t ntiles = 0;
-    // descriptor bases (warp-uniform); per-MMA work is one constant add per operand
-    const uint64_t q_desc = umma_desc(kmaj, smem_u32(sm.q)), do_desc = umma_desc(kmaj, smem_u32(sm.dout));
-    const uint64_t k_kdesc0 = umma_desc(kmaj, smem_u32(sm.k[0])), k_mndesc0 = umma_desc(mnmaj, smem_u32(sm.k[0]));
-    const uint64_t v_kdesc0 = umma_desc(kmaj, smem_u32(sm.v[0]));
-    constexpr uint32_t SLOT16 = DqSmem<D>::TILE >> 4;
-    while (state[0] != 3 || state[1] != 3) {
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        if (state[w] == 3) continue;
-        if (state[w] == -1) {
-          const int r = feed.fetch(w, lane, tl[w], jj[w]);
-          if (r == 0) continue;
-          state[w] = r == 1 ? 0 : 3;
-          if (r != 1) continue;
-        }
-        const uint32_t g = tile_base + jj[w];
-        const uint32_t ks = g % 3, kph = (g / 3) & 1, vs = g % 2, vph = (g / 2) & 1;
-        const uint64_t kd = k_kdesc0 + uint64_t(ks * SLOT16), kmn = k_mndesc0 + uint64_t(ks * SLOT16);
-        const uint64_t vd = v_kdesc0 + uint64_t(vs * SLOT16);
-        if (state[w] == 0) {
-          if (!warp_test(&sm.k_full[ks], kph, lane)) continue;
-          tc_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-              const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
-              umma_ss(x_tm[w], umma_desc_add(q_desc, off), umma_desc_add(kd, off), idesc_s, kk > 0);
-            }
-            umma_commit(&sm.s_full[w]);
-          }
-          __syncwarp();
-          state[w] = 1;
-        } else if (state[w] == 1) {
-          if (!warp_test(&sm.v_full[vs], vph, lane)) continue;
-          if (!warp_test(&sm.s_taken[w], cnt[w] & 1, lane)) continue;
-          tc_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-              const uint32_t off = (kk / 4) * SUB128 + (kk % 4) * 32;
-              umma_ss(x_tm[w], umma_desc_add(do_desc, off), umma_desc_add(vd, off), idesc_s, kk > 0);
-            }
-            umma_commit(&sm.dp_full[w]);
-            umma_commit(&sm.v_empty[vs]);
-          }
-          __syncwarp();
-          state[w] = 2;
-        } else {
-          if (!warp_test(&sm.ds_ready[w], cnt[w] & 1, lane)) continue;
-          if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 610);
-          tc_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < 128 / 16; ++kk) {
-              umma_ts(dq_tm, x_tm[w] + kk * 8, umma_desc_add(kmn, kk * 2048), idesc_dq,
-                      (dq_started || kk > 0) ? 1u : 0u);
-            }
-            umma_commit(&sm.k_empty[ks]);
-          }
-          __syncwarp();
-          dq_started = true;
-          cnt[w]++;
-          ntiles++;
-          state[w] = -1;
-        }
-      }
-    }
-    if (!dq_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 611);
-    umma_commit_w(&sm.dq_done);
-    umma_commit_w(&sm.qdo_empty);
-    tile_base += ntiles;
-  }
-}
-
-// Two-issuer variant of the dQ kernel (same reasoning as dkv_issue_s below: the single issuing warp's polling loop, not
-// the tensor pipe, paced the kernel).  The logits live in three rotating TMEM regions (tile g of this CTA's lifetime
+// Two issuing warps (same reasoning as dkv_issue_s below: a single issuing warp's polling loop, not the tensor pipe,
+// paced the first version of this kernel).  The logits live in three rotating TMEM regions (tile g of this CTA's lifetime
 // uses region g % 3, which is also its K smem stage), every barrier between the issuers and the warpgroups is indexed
 // by region with parity (g / 3) & 1, and all waits are blocking waits in program order:
 //   warp 9  : S(j) = Q K^T into region r, dP(j) = dO V^T into region r once the warpgroup holds S(j) in registers
@@ -411,15 +263,13 @@ __device__ __forceinline__ void dq_issue_dq(DqSmem<D>& sm, const AttnBwdParams& 
   }
 }
 
-// POLYQ of every 4 logit pairs take their exponential on the FMA pipe (poly_exp2x2, ptx.cuh) instead of the MUFU.
-template <int D, bool BF16, bool TWO, int POLYQ>
+template <int D, bool BF16>
 __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem) {
   const int wg_tid = threadIdx.x - 128 * W;
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
-  uint32_t x_tm = tmem + W * 128 + lane_off;
   const uint32_t dq_tm = tmem + 256 + lane_off;
   const int lane = lane_id();
-  uint32_t cnt = 0, n_item = 0, tile_base = 0;
+  uint32_t n_item = 0, tile_base = 0;
 
   const bool clamp = p.softclamp > 0.f;
   const float mul = clamp ? 1.f : p.scale * kLog2e;
@@ -447,25 +297,15 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
     while (scan.next(lane, t)) {
       const uint32_t jcur = jj++;
       if ((jcur & 1u) != (uint32_t)W) continue;
-      // barriers of this tile: per stream (parity = tiles done by this warpgroup) or, with two issuers, per region
-      uint64_t *b_s_full, *b_s_taken, *b_dp_full, *b_ds_ready;
-      uint32_t bpar;
-      if constexpr (TWO) {
-        const uint32_t g = tile_base + jcur;
-        const uint32_t r = g % 3;
-        bpar = (g / 3) & 1;
-        x_tm = tmem + dq_region_col(r) + lane_off;
-        b_s_full = &sm.r_s_full[r];
-        b_s_taken = &sm.r_s_taken[r];
-        b_dp_full = &sm.r_dp_full[r];
-        b_ds_ready = &sm.r_ds_ready[r];
-      } else {
-        bpar = cnt & 1;
-        b_s_full = &sm.s_full[0] + W;
-        b_s_taken = &sm.s_taken[0] + W;
-        b_dp_full = &sm.dp_full[0] + W;
-        b_ds_ready = &sm.ds_ready[0] + W;
-      }
+      // barriers of this tile are indexed by its TMEM region
+      const uint32_t g = tile_base + jcur;
+      const uint32_t r = g % 3;
+      const uint32_t bpar = (g / 3) & 1;
+      const uint32_t x_tm = tmem + dq_region_col(r) + lane_off;
+      uint64_t* const b_s_full = &sm.r_s_full[r];
+      uint64_t* const b_s_taken = &sm.r_s_taken[r];
+      uint64_t* const b_dp_full = &sm.r_dp_full[r];
+      uint64_t* const b_ds_ready = &sm.r_ds_ready[r];
       mbar_wait(b_s_full, bpar, 700 + W);
       tc_fence_after();
       uint32_t sr[128];
@@ -507,7 +347,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
 #pragma unroll
         for (int j = 0; j < 128; j += 2) {
           const float2 a = ffma2(make_float2(__uint_as_float(sr[j]), __uint_as_float(sr[j + 1])), mul2, nl2);
-          const float2 e = (((j >> 1) & 3) < POLYQ) ? poly_exp2x2(a) : make_float2(fast_exp2(a.x), fast_exp2(a.y));
+          const float2 e = make_float2(fast_exp2(a.x), fast_exp2(a.y));
           sr[j] = __float_as_uint(e.x);
           sr[j + 1] = __float_as_uint(e.y);
         }
@@ -578,7 +418,6 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(b_ds_ready);
-      cnt++;
     }
     tile_base += jj;
 
@@ -618,7 +457,7 @@ __device__ __forceinline__ void dq_softmax(DqSmem<D>& sm, const AttnBwdParams& p
   }
 }
 
-template <int D, bool BF16, bool TWO, int POLYQ>
+template <int D, bool BF16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_constant__ CUtensorMap map_kv,
                    const __grid_constant__ AttnBwdParams p) {
@@ -635,10 +474,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_cons
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.v_full[i], 1);
       mbar_init(&sm.v_empty[i], 1);
-      mbar_init(&sm.s_full[i], 1);
-      mbar_init(&sm.s_taken[i], 128);
-      mbar_init(&sm.dp_full[i], 1);
-      mbar_init(&sm.ds_ready[i], 128);
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(&sm.r_s_full[i], 1);
@@ -662,16 +497,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qd, const __grid_cons
   if (warp >= 8) {  // control warps on the highest warp ids: the scheduler favours them
     setmaxnreg_dec<120>();
     if (warp == 8) dq_producer<D>(sm, p, &map_qd, &map_kv);
-    if (warp == 9) {
-      if constexpr (TWO) dq_issue_sdp<D, BF16>(sm, p, tmem);
-      else dq_mma<D, BF16>(sm, p, tmem);
-    }
-    if (warp == 10) {
-      if constexpr (TWO) dq_issue_dq<D, BF16>(sm, p, tmem);
-    }
+    if (warp == 9) dq_issue_sdp<D, BF16>(sm, p, tmem);
+    if (warp == 10) dq_issue_dq<D, BF16>(sm, p, tmem);
   } else {
     setmaxnreg_inc<192>();
-    dq_softmax<D, BF16, TWO, POLYQ>(sm, p, warp < 4 ? 0 : 1, tmem);
+    dq_softmax<D, BF16>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
   tc_fence_before();
   __syncthreads();
@@ -696,17 +526,9 @@ struct DkvSmem {
   alignas(16) float delta[QSTAGES][64];
   uint64_t kv_full, kv_empty;
   uint64_t qd_full[QSTAGES], qd_empty[QSTAGES];
-  uint64_t sdp_full[2], pds_ready[2];
-  uint64_t s_full[2], s_free[2], dp_full[2];  // pipelined variant
-  uint64_t dq_full[2], x_free[2];             // one-kernel variant (MODE 3)
+  uint64_t s_full[2], s_free[2], dp_full[2], pds_ready[2];
   uint64_t acc_done, epi_done;
   uint32_t tmem_base;
-};
-
-// MODE 3 adds one [128 keys x 64 queries] 16-bit tile per stream: dS^T as the B operand of dQ^T = K^T dS^T
-template <int D>
-struct DkvFusedSmem : DkvSmem<D> {
-  alignas(1024) uint8_t ds[2][128 * 128];
 };
 
 struct DkvItem {
@@ -796,228 +618,7 @@ __device__ __forceinline__ void dkv_producer(DkvSmem<D>& sm, const AttnBwdParams
   }
 }
 
-template <int D, bool BF16>
-__device__ __forceinline__ void dkv_mma(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);   // S^T, dP^T : N = 64 queries
-  constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);  // dV, dK    : N = D, B MN-major
-  constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
-  constexpr uint64_t mnmaj64 = umma_smem_desc_hi_lo(SUB64, 1024, UMMA_LAYOUT_SW128);
-  // TMEM: stream w: S^T at w*128 (P^T aliases its first 32 columns), dP^T at w*128+64 (dS^T aliases it)
-  const int lane = lane_id();
-  const uint32_t tmem = warp_uniform(tmem_in);
-  const uint32_t st_tm[2] = {tmem + 0, tmem + 128};
-  const uint32_t dpt_tm[2] = {tmem + 64, tmem + 192};
-  const uint32_t dk_tm = tmem + 256, dv_tm = tmem + 256 + D;
-
-  uint32_t n_item = 0, tile_base = 0;
-  uint32_t cnt[2] = {0, 0};
-  const int total = dkv_num_items(p);
-  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
-    DkvItem it;
-    dkv_decode(p, idx, it);
-    mbar_wait(&sm.kv_full, n_item & 1, 900);
-    tc_fence_after();
-
-    StreamFeeder<DkvScan> feed;
-    dkv_init_scan(feed.scan, p, it);
-    ScanTile tl[2];
-    int state[2] = {-1, -1};  // -1: need a tile, 0: need S^T/dP^T, 1: need dV/dK, 3: done
-    uint32_t jj[2] = {0, 0};
-    bool acc_started = false;
-    uint32_t ntiles = 0;
-    const uint64_t k_desc = umma_desc(kmaj, smem_u32(sm.k)), v_desc = umma_desc(kmaj, smem_u32(sm.v));
-    const uint64_t q_kdesc0 = umma_desc(kmaj, smem_u32(sm.q[0])), q_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.q[0]));
-    const uint64_t do_kdesc0 = umma_desc(kmaj, smem_u32(sm.dout[0])),
-                   do_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.dout[0]));
-    constexpr uint32_t STAGE16 = DkvSmem<D>::Q_TILE >> 4;
-    while (state[0] != 3 || state[1] != 3) {
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        if (state[w] == 3) continue;
-        if (state[w] == -1) {
-          const int r = feed.fetch(w, lane, tl[w], jj[w]);
-          if (r == 0) continue;
-          state[w] = r == 1 ? 0 : 3;
-          if (r != 1) continue;
-        }
-        const uint32_t g = tile_base + jj[w];
-        const uint32_t st = g % QSTAGES, ph = (g / QSTAGES) & 1;
-        const uint64_t qk = q_kdesc0 + uint64_t(st * STAGE16), qmn = q_mndesc0 + uint64_t(st * STAGE16);
-        const uint64_t dok = do_kdesc0 + uint64_t(st * STAGE16), domn = do_mndesc0 + uint64_t(st * STAGE16);
-        if (state[w] == 0) {
-          if (!warp_test(&sm.qd_full[st], ph, lane)) continue;
-          tc_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-              const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
-              const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
-              umma_ss(st_tm[w], umma_desc_add(k_desc, offk), umma_desc_add(qk, offq), idesc_s, kk > 0);
-            }
-#pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-              const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
-              const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
-              umma_ss(dpt_tm[w], umma_desc_add(v_desc, offk), umma_desc_add(dok, offq), idesc_s, kk > 0);
-            }
-            umma_commit(&sm.sdp_full[w]);
-          }
-          __syncwarp();
-          state[w] = 1;
-        } else {
-          if (!warp_test(&sm.pds_ready[w], cnt[w] & 1, lane)) continue;
-          if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 910);
-          tc_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < 64 / 16; ++kk) {
-              umma_ts(dv_tm, st_tm[w] + kk * 8, umma_desc_add(domn, kk * 2048), idesc_acc,
-                      (acc_started || kk > 0) ? 1u : 0u);
-            }
-#pragma unroll
-            for (int kk = 0; kk < 64 / 16; ++kk) {
-              umma_ts(dk_tm, dpt_tm[w] + kk * 8, umma_desc_add(qmn, kk * 2048), idesc_acc,
-                      (acc_started || kk > 0) ? 1u : 0u);
-            }
-            umma_commit(&sm.qd_empty[st]);
-          }
-          __syncwarp();
-          acc_started = true;
-          cnt[w]++;
-          ntiles++;
-          state[w] = -1;
-        }
-      }
-    }
-    if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 911);
-    umma_commit_w(&sm.acc_done);
-    umma_commit_w(&sm.kv_empty);
-    tile_base += ntiles;
-  }
-}
-
-// Pipelined issue order (PIPE = true).  Per stream w the TMEM blocks are X_w (S^T) and Y_w (dP^T, later P^T | dS^T
-// packed into its 64 columns).  X_w is free as soon as the warpgroup has pulled S^T(i) into registers (s_free), so
-// S^T(i+1) is computed while the warpgroup still works on tile i; dP^T(i+1) follows dV/dK(i) in the tensor pipe's FIFO
-// order (both touch Y_w).  The chain of one stream shrinks from  MMA -> softmax -> MMA  to  half a softmax -> MMA.
-template <int D, bool BF16>
-__device__ __forceinline__ void dkv_mma_pipe(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);
-  constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);
-  constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
-  constexpr uint64_t mnmaj64 = umma_smem_desc_hi_lo(SUB64, 1024, UMMA_LAYOUT_SW128);
-  const int lane = lane_id();
-  const uint32_t tmem = warp_uniform(tmem_in);
-  const uint32_t x_tm[2] = {tmem + 0, tmem + 128};
-  const uint32_t y_tm[2] = {tmem + 64, tmem + 192};
-  const uint32_t dk_tm = tmem + 256, dv_tm = tmem + 256 + D;
-
-  uint32_t n_item = 0, tile_base = 0;
-  // cumulative per-stream counters: tiles fetched, S^T issued, dP^T issued, dV/dK issued
-  uint32_t nf[2] = {0, 0}, iS[2] = {0, 0}, iP[2] = {0, 0}, iB[2] = {0, 0};
-  uint32_t jq[2][2] = {{0, 0}, {0, 0}};  // sequence number of the (at most two) tiles in flight per stream
-  const int total = dkv_num_items(p);
-  for (int idx = blockIdx.x; idx < total; idx += gridDim.x, ++n_item) {
-    DkvItem it;
-    dkv_decode(p, idx, it);
-    mbar_wait(&sm.kv_full, n_item & 1, 900);
-    tc_fence_after();
-
-    StreamFeeder<DkvScan> feed;
-    dkv_init_scan(feed.scan, p, it);
-    bool end[2] = {false, false};
-    bool acc_started = false;
-    uint32_t ntiles = 0;
-    const uint64_t k_desc = umma_desc(kmaj, smem_u32(sm.k)), v_desc = umma_desc(kmaj, smem_u32(sm.v));
-    const uint64_t q_kdesc0 = umma_desc(kmaj, smem_u32(sm.q[0])), q_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.q[0]));
-    const uint64_t do_kdesc0 = umma_desc(kmaj, smem_u32(sm.dout[0])),
-                   do_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.dout[0]));
-    constexpr uint32_t STAGE16 = DkvSmem<D>::Q_TILE >> 4;
-    while (!(end[0] && end[1] && iB[0] == nf[0] && iB[1] == nf[1])) {
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        if (!end[w] && nf[w] - iB[w] < 2u) {
-          ScanTile tl;
-          uint32_t j = 0;
-          const int r = feed.fetch(w, lane, tl, j);
-          if (r == 1) {
-            jq[w][nf[w] & 1] = j;
-            nf[w]++;
-          } else if (r == -1) {
-            end[w] = true;
-          }
-        }
-        // dV += P^T dO, dK += dS^T Q   (tile iB)
-        if (iB[w] != iP[w] && warp_test(&sm.pds_ready[w], iB[w] & 1, lane)) {
-          if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 910);
-          tc_fence_after();
-          const uint32_t st = (tile_base + jq[w][iB[w] & 1]) % QSTAGES;
-          const uint64_t qmn = q_mndesc0 + uint64_t(st * STAGE16), domn = do_mndesc0 + uint64_t(st * STAGE16);
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < 64 / 16; ++kk) {
-              umma_ts(dv_tm, y_tm[w] + kk * 8, umma_desc_add(domn, kk * 2048), idesc_acc,
-                      (acc_started || kk > 0) ? 1u : 0u);
-            }
-#pragma unroll
-            for (int kk = 0; kk < 64 / 16; ++kk) {
-              umma_ts(dk_tm, y_tm[w] + 32 + kk * 8, umma_desc_add(qmn, kk * 2048), idesc_acc,
-                      (acc_started || kk > 0) ? 1u : 0u);
-            }
-            umma_commit(&sm.qd_empty[st]);
-          }
-          __syncwarp();
-          acc_started = true;
-          iB[w]++;
-          ntiles++;
-        }
-        // dP^T = V dO^T   (tile iP; Y_w is free once dV/dK of the previous tile sit in front of it in the FIFO)
-        if (iP[w] != iS[w] && iP[w] == iB[w]) {
-          const uint32_t st = (tile_base + jq[w][iP[w] & 1]) % QSTAGES;
-          const uint64_t dok = do_kdesc0 + uint64_t(st * STAGE16);
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-              const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
-              const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
-              umma_ss(y_tm[w], umma_desc_add(v_desc, offk), umma_desc_add(dok, offq), idesc_s, kk > 0);
-            }
-            umma_commit(&sm.dp_full[w]);
-          }
-          __syncwarp();
-          iP[w]++;
-        }
-        // S^T = K Q^T   (tile iS; needs its Q tile in smem and X_w drained into registers)
-        if (iS[w] != nf[w]) {
-          const uint32_t g = tile_base + jq[w][iS[w] & 1];
-          const uint32_t st = g % QSTAGES, ph = (g / QSTAGES) & 1;
-          const bool x_free = iS[w] == 0u || warp_test(&sm.s_free[w], (iS[w] - 1u) & 1, lane);
-          if (x_free && warp_test(&sm.qd_full[st], ph, lane)) {
-            tc_fence_after();
-            const uint64_t qk = q_kdesc0 + uint64_t(st * STAGE16);
-            if (elect_one()) {
-#pragma unroll
-              for (int kk = 0; kk < D / 16; ++kk) {
-                const uint32_t offk = (kk / 4) * SUB128 + (kk % 4) * 32;
-                const uint32_t offq = (kk / 4) * SUB64 + (kk % 4) * 32;
-                umma_ss(x_tm[w], umma_desc_add(k_desc, offk), umma_desc_add(qk, offq), idesc_s, kk > 0);
-              }
-              umma_commit(&sm.s_full[w]);
-            }
-            __syncwarp();
-            iS[w]++;
-          }
-        }
-      }
-    }
-    if (!acc_started) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 911);
-    umma_commit_w(&sm.acc_done);
-    umma_commit_w(&sm.kv_empty);
-    tile_base += ntiles;
-  }
-}
-
-// Two-issuer variant (MODE 2).  Profiling the single-issuer kernels showed the MMA-issuing warp executing ~380
+// Two issuing warps.  Profiling the first, single-issuer version of this kernel showed the MMA-issuing warp executing ~380
 // instructions of polling / bookkeeping per 128 x 64 step while the tensor pipe back-pressured it only 10 % of the time:
 // the issuer's own control flow, not the tensor core, paced the kernel.  Here the work is split by TMEM block instead of
 // by stream, which makes every wait a plain blocking mbarrier wait in program order (no state machine, no scanner in
@@ -1026,7 +627,7 @@ __device__ __forceinline__ void dkv_mma_pipe(DkvSmem<D>& sm, const AttnBwdParams
 //   warp 10 "acc issuer" : dP^T(j) into Y_w, dV/dK(j) from Y_w   gated by qd_full(stage j), pds_ready[w]
 // The two warps never touch the same TMEM block, and only warp 10 accumulates into dK/dV, so no cross-warp ordering of
 // tcgen05.mma is relied upon.
-template <int D, bool BF16, bool FUSED>
+template <int D, bool BF16>
 __device__ __forceinline__ void dkv_issue_s(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);
   constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
@@ -1051,9 +652,8 @@ __device__ __forceinline__ void dkv_issue_s(DkvSmem<D>& sm, const AttnBwdParams&
       const uint32_t g = tile_base + j;
       const uint32_t st = g % QSTAGES, ph = (g / QSTAGES) & 1;
       mbar_wait(&sm.qd_full[st], ph, 920 + st);
-      // X_w is free once S^T has been pulled into registers — or, in the one-kernel variant, once dQ^T (which reuses
-      // the block) has been drained to global memory
-      if (c_s[w] > 0) mbar_wait(FUSED ? &sm.x_free[w] : &sm.s_free[w], (c_s[w] - 1u) & 1, 930 + w);
+      // X_w is free once S^T has been pulled into registers
+      if (c_s[w] > 0) mbar_wait(&sm.s_free[w], (c_s[w] - 1u) & 1, 930 + w);
       tc_fence_after();
       const uint32_t x_tm = tmem + w * 128u;
       const uint64_t qk = q_kdesc0 + uint64_t(st * STAGE16);
@@ -1074,9 +674,8 @@ __device__ __forceinline__ void dkv_issue_s(DkvSmem<D>& sm, const AttnBwdParams&
   }
 }
 
-template <int D, bool BF16, bool FUSED>
-__device__ __forceinline__ void dkv_issue_acc(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in,
-                                              uint32_t ds_smem_base) {
+template <int D, bool BF16>
+__device__ __forceinline__ void dkv_issue_acc(DkvSmem<D>& sm, const AttnBwdParams& p, uint32_t tmem_in) {
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);
   constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);
   constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
@@ -1142,20 +741,6 @@ __device__ __forceinline__ void dkv_issue_acc(DkvSmem<D>& sm, const AttnBwdParam
           umma_ts(dk_tm, y_tm + 32 + kk * 8, umma_desc_add(qmn, kk * 2048), idesc_acc, kk > 0 ? 1u : acc0);
         }
         umma_commit(&sm.qd_empty[st]);
-        if constexpr (FUSED) {
-          // dQ^T[d, q] = K^T[d, keys] dS^T[keys, q]: A = the K tile read MN-major (like V in the forward's P V),
-          // B = the dS^T tile the warpgroup wrote to shared memory; D reuses X_w (S^T is long in registers)
-          constexpr uint32_t idesc_dqt = umma_idesc_bf16(D, 64, 1, 1, BF16 ? 1 : 0);
-          constexpr uint64_t mn_static = umma_smem_desc_hi_lo(SUB128, 1024, UMMA_LAYOUT_SW128);
-          const uint64_t k_mn = umma_desc(mn_static, smem_u32(sm.k));
-          const uint64_t ds_mn = umma_desc(mn_static, ds_smem_base + w * (128 * 128));
-          const uint32_t x_tm = tmem + w * 128u;
-#pragma unroll
-          for (int kk = 0; kk < 128 / 16; ++kk) {
-            umma_ss(x_tm, umma_desc_add(k_mn, kk * 2048), umma_desc_add(ds_mn, kk * 2048), idesc_dqt, kk > 0);
-          }
-          umma_commit(&sm.dq_full[w]);
-        }
       }
       __syncwarp();
       c_b[w]++;
@@ -1168,9 +753,8 @@ __device__ __forceinline__ void dkv_issue_acc(DkvSmem<D>& sm, const AttnBwdParam
   }
 }
 
-template <int D, bool BF16, bool PIPE, int POLYQ, bool FUSED>
-__device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem,
-                                            uint8_t* ds_smem) {
+template <int D, bool BF16>
+__device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams& p, const int W, uint32_t tmem) {
   const int wg_tid = threadIdx.x - 128 * W;
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
   const uint32_t st_tm = tmem + W * 128 + lane_off;
@@ -1204,23 +788,13 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
       if ((jj & 1u) != (uint32_t)W) continue;
       const uint32_t stg = (tile_base + jj) % QSTAGES;
       uint32_t sr[64], dp[64];
-      if constexpr (PIPE) {
-        mbar_wait((&sm.s_full[0] + W), cnt & 1, 1000 + W);
-        tc_fence_after();
-        tmem_ld32(st_tm + 0, sr + 0);
-        tmem_ld32(st_tm + 32, sr + 32);
-        tc_wait_ld();
-        tc_fence_before();
-        if constexpr (!FUSED) mbar_arrive((&sm.s_free[0] + W));  // X_w may take S^T of this stream's next tile now
-      } else {
-        mbar_wait((&sm.sdp_full[0] + W), cnt & 1, 1000 + W);
-        tc_fence_after();
-        tmem_ld32(st_tm + 0, sr + 0);
-        tmem_ld32(st_tm + 32, sr + 32);
-        tc_wait_ld();
-        tmem_ld32(dpt_tm + 0, dp + 0);  // dP^T stays in flight while the exponentials below run
-        tmem_ld32(dpt_tm + 32, dp + 32);
-      }
+      mbar_wait((&sm.s_full[0] + W), cnt & 1, 1000 + W);
+      tc_fence_after();
+      tmem_ld32(st_tm + 0, sr + 0);
+      tmem_ld32(st_tm + 32, sr + 32);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive((&sm.s_free[0] + W));  // X_w may take S^T of this stream's next tile now
 
       const int c0 = t.idx * 64;
       const float4* l4 = reinterpret_cast<const float4*>(sm.lse2[stg]);
@@ -1238,10 +812,7 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
                                    make_float2(-lv.x, -lv.y));
           const float2 a23 = ffma2(make_float2(__uint_as_float(sr[q4 * 4 + 2]), __uint_as_float(sr[q4 * 4 + 3])), mul2,
                                    make_float2(-lv.z, -lv.w));
-          const float2 e01 = (((2 * q4) & 3) < POLYQ) ? poly_exp2x2(a01) : make_float2(fast_exp2(a01.x), fast_exp2(a01.y));
-          const float2 e23 =
-              (((2 * q4 + 1) & 3) < POLYQ) ? poly_exp2x2(a23) : make_float2(fast_exp2(a23.x), fast_exp2(a23.y));
-          const float p0 = e01.x, p1 = e01.y, p2 = e23.x, p3 = e23.y;
+          const float p0 = fast_exp2(a01.x), p1 = fast_exp2(a01.y), p2 = fast_exp2(a23.x), p3 = fast_exp2(a23.y);
           sr[q4 * 4 + 0] = __float_as_uint(p0);
           sr[q4 * 4 + 1] = __float_as_uint(p1);
           sr[q4 * 4 + 2] = __float_as_uint(p2);
@@ -1249,12 +820,10 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
           pw[q4 * 2] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
           pw[q4 * 2 + 1] = BF16 ? pack_bf16x2(p2, p3) : pack_f16x2(p2, p3);
         }
-        if constexpr (PIPE) {
-          mbar_wait((&sm.dp_full[0] + W), cnt & 1, 1004 + W);
-          tc_fence_after();
-          tmem_ld32(dpt_tm + 0, dp + 0);
-          tmem_ld32(dpt_tm + 32, dp + 32);
-        }
+        mbar_wait((&sm.dp_full[0] + W), cnt & 1, 1004 + W);
+        tc_fence_after();
+        tmem_ld32(dpt_tm + 0, dp + 0);
+        tmem_ld32(dpt_tm + 32, dp + 32);
         tc_wait_ld();  // dP^T has landed
 #pragma unroll
         for (int q4 = 0; q4 < 16; ++q4) {
@@ -1269,12 +838,10 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
           dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(e23.x, e23.y) : pack_f16x2(e23.x, e23.y);
         }
       } else {
-        if constexpr (PIPE) {
-          mbar_wait((&sm.dp_full[0] + W), cnt & 1, 1004 + W);
-          tc_fence_after();
-          tmem_ld32(dpt_tm + 0, dp + 0);
-          tmem_ld32(dpt_tm + 32, dp + 32);
-        }
+        mbar_wait((&sm.dp_full[0] + W), cnt & 1, 1004 + W);
+        tc_fence_after();
+        tmem_ld32(dpt_tm + 0, dp + 0);
+        tmem_ld32(dpt_tm + 32, dp + 32);
         tc_wait_ld();  // dP^T has landed
         const int split = p.pos.seg_len - c0;
         const int a0 = p.pos.base0[t.owner] + p.pos.stride * c0 + p.q_pos_offset;
@@ -1319,48 +886,12 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
           dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(dd[2], dd[3]) : pack_f16x2(dd[2], dd[3]);
         }
       }
-      if constexpr (PIPE) {  // P^T | dS^T share the dP^T block; the S^T block already belongs to the next tile
-        tmem_st32(dpt_tm, pw);
-        tmem_st32(dpt_tm + 32, dw);
-      } else {
-        tmem_st32(st_tm, pw);
-        tmem_st32(dpt_tm, dw);
-      }
-      if constexpr (FUSED) {
-        // dS^T row of this key into shared memory, 128B swizzle applied by hand (chunk c of row r sits at c ^ (r % 8))
-        uint8_t* row = ds_smem + W * (128 * 128) + wg_tid * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(row + ((c ^ (wg_tid & 7)) << 4)) =
-              make_uint4(dw[4 * c], dw[4 * c + 1], dw[4 * c + 2], dw[4 * c + 3]);
-        fence_proxy_async_shared();
-      }
+      // P^T | dS^T share the dP^T block; the S^T block already belongs to the next tile
+      tmem_st32(dpt_tm, pw);
+      tmem_st32(dpt_tm + 32, dw);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive((&sm.pds_ready[0] + W));
-      if constexpr (FUSED) {
-        // drain dQ^T (lane = d index, 64 query columns) into the fp32 accumulator: for a fixed query row the 32 lanes
-        // of a warp hit 32 consecutive floats
-        mbar_wait((&sm.dq_full[0] + W), cnt & 1, 1008 + W);
-        tc_fence_after();
-        uint32_t g0[32], g1[32];
-        tmem_ld32(st_tm + 0, g0);
-        tmem_ld32(st_tm + 32, g1);
-        tc_wait_ld();
-        tc_fence_before();
-        mbar_arrive((&sm.x_free[0] + W));
-        const int head = t.rep * p.kv_heads + it.kvh;
-        const int q0 = t.idx * 64;
-        float* base = p.dq_acc + (((size_t)it.b * p.n_q + q0) * p.heads + head) * D + wg_tid;
-        const size_t row_stride = (size_t)p.heads * D;
-        const int nrow = min(64, p.n_q - q0);
-#pragma unroll
-        for (int qq = 0; qq < 32; ++qq)
-          if (qq < nrow) red_add_f32(base + qq * row_stride, __uint_as_float(g0[qq]) * p.scale);
-#pragma unroll
-        for (int qq = 0; qq < 32; ++qq)
-          if (qq + 32 < nrow) red_add_f32(base + (qq + 32) * row_stride, __uint_as_float(g1[qq]) * p.scale);
-      }
       cnt++;
     }
     tile_base += jn;  // both warpgroups walk the whole sequence, so the stage ring stays in step
@@ -1403,32 +934,25 @@ __device__ __forceinline__ void dkv_softmax(DkvSmem<D>& sm, const AttnBwdParams&
   }
 }
 
-template <int D, bool BF16, int MODE, int POLYQ>
+template <int D, bool BF16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_constant__ CUtensorMap map_kv,
                      const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr bool FUSED = MODE == 3;  // two issuers + dQ^T in the same kernel (experimental)
-  constexpr bool TWO_ISSUERS = MODE >= 2;
-  DkvFusedSmem<D>& fsm =
-      *reinterpret_cast<DkvFusedSmem<D>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  DkvSmem<D>& sm = fsm;  // the dS^T tiles behind it are only touched (and only allocated) when FUSED
+  DkvSmem<D>& sm = *reinterpret_cast<DkvSmem<D>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x / 32;
   if (threadIdx.x == 0) {
     mbar_init(&sm.kv_full, 1);
-    mbar_init(&sm.kv_empty, TWO_ISSUERS ? 2 : 1);
+    mbar_init(&sm.kv_empty, 2);
     for (int i = 0; i < QSTAGES; ++i) {
       mbar_init(&sm.qd_full[i], 1);
       mbar_init(&sm.qd_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&sm.sdp_full[i], 1);
       mbar_init(&sm.pds_ready[i], 128);
       mbar_init(&sm.s_full[i], 1);
       mbar_init(&sm.s_free[i], 128);
       mbar_init(&sm.dp_full[i], 1);
-      mbar_init(&sm.dq_full[i], 1);
-      mbar_init(&sm.x_free[i], 128);
     }
     mbar_init(&sm.acc_done, 1);
     mbar_init(&sm.epi_done, 256);
@@ -1445,17 +969,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_
   if (warp >= 8) {  // control warps on the highest warp ids: the scheduler favours them
     setmaxnreg_dec<120>();
     if (warp == 8) dkv_producer<D>(sm, p, &map_qd64, &map_kv);
-    if (warp == 9) {
-      if constexpr (TWO_ISSUERS) dkv_issue_s<D, BF16, FUSED>(sm, p, tmem);
-      else if constexpr (MODE == 1) dkv_mma_pipe<D, BF16>(sm, p, tmem);
-      else dkv_mma<D, BF16>(sm, p, tmem);
-    }
-    if (warp == 10) {
-      if constexpr (TWO_ISSUERS) dkv_issue_acc<D, BF16, FUSED>(sm, p, tmem, FUSED ? smem_u32(fsm.ds[0]) : 0u);
-    }
+    if (warp == 9) dkv_issue_s<D, BF16>(sm, p, tmem);
+    if (warp == 10) dkv_issue_acc<D, BF16>(sm, p, tmem);
   } else {
     setmaxnreg_inc<192>();
-    dkv_softmax<D, BF16, (MODE != 0), POLYQ, FUSED>(sm, p, warp < 4 ? 0 : 1, tmem, FUSED ? fsm.ds[0] : nullptr);
+    dkv_softmax<D, BF16>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
   tc_fence_before();
   __syncthreads();
@@ -1516,30 +1034,11 @@ __global__ void bwd_prep_kernel(const uint16_t* __restrict__ q, const uint16_t* 
 
 }  // namespace
 
-// RAB_BWD_EXP_POLY=1 (experimental, default 0): a quarter of the backward's P-recompute exponentials on the FMA pipe,
-// the switch that gave the forward +5 %; not yet timed for the backward.
-static bool bwd_exp_poly() {
-  static const bool on = [] {
-    const char* e = std::getenv("RAB_BWD_EXP_POLY");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
-
 template <int D>
 void launch_attn_bwd_dq(const CUtensorMap& map_qd, const CUtensorMap& map_kv, const AttnBwdParams& p, int num_sms,
                         cudaStream_t stream) {
-  // default: two issuing warps + three rotating TMEM regions (see dq_issue_sdp); RAB_DQ_TWO=0: single polling issuer
-  // (kept for A/B measurements: 13.1 -> 11.8 ms at n=65536, h=8)
-  static const bool two = [] {
-    const char* e = std::getenv("RAB_DQ_TWO");
-    return e == nullptr || e[0] != '0';
-  }();
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const AttnBwdParams);
-  Kern kern;
-  if (!two) kern = p.is_bf16 ? attn_bwd_dq_kernel<D, true, false, 0> : attn_bwd_dq_kernel<D, false, false, 0>;
-  else if (bwd_exp_poly()) kern = p.is_bf16 ? attn_bwd_dq_kernel<D, true, true, 1> : attn_bwd_dq_kernel<D, false, true, 1>;
-  else kern = p.is_bf16 ? attn_bwd_dq_kernel<D, true, true, 0> : attn_bwd_dq_kernel<D, false, true, 0>;
+  Kern kern = p.is_bf16 ? attn_bwd_dq_kernel<D, true> : attn_bwd_dq_kernel<D, false>;
   const size_t smem = sizeof(DqSmem<D>) + 1024;
   cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "bwd_dq smem attr");
   const int items = p.batch * p.heads * ((p.n_q + 127) / 128);
@@ -1551,24 +1050,9 @@ void launch_attn_bwd_dq(const CUtensorMap& map_qd, const CUtensorMap& map_kv, co
 template <int D>
 void launch_attn_bwd_dkdv(const CUtensorMap& map_qd64, const CUtensorMap& map_kv, const AttnBwdParams& p,
                           int num_sms, cudaStream_t stream) {
-  // RAB_DKDV_PIPE: 0 = one issuer, S^T/dP^T together; 1 = one issuer, pipelined; 2 (default) = two issuers, see
-  // dkv_issue_s.  0 and 1 are kept for A/B measurements (n=65536, h=8: 22.9 / 22.3 / 15.2 ms).
-  static const int mode = [] {
-    const char* e = std::getenv("RAB_DKDV_PIPE");
-    return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? int(e[0] - '0') : 2;
-  }();
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const AttnBwdParams);
-  Kern kern;
-  bool fused = false;
-  if constexpr (D == 128) fused = p.dq_acc != nullptr;
-  if (fused) {
-    if constexpr (D == 128) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<128, true, 3, 0> : attn_bwd_dkdv_kernel<128, false, 3, 0>;
-  } else if (mode == 2 && bwd_exp_poly())
-    kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 2, 1> : attn_bwd_dkdv_kernel<D, false, 2, 1>;
-  else if (mode == 2) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 2, 0> : attn_bwd_dkdv_kernel<D, false, 2, 0>;
-  else if (mode == 1) kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 1, 0> : attn_bwd_dkdv_kernel<D, false, 1, 0>;
-  else kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true, 0, 0> : attn_bwd_dkdv_kernel<D, false, 0, 0>;
-  const size_t smem = (fused ? sizeof(DkvFusedSmem<D>) : sizeof(DkvSmem<D>)) + 1024;
+  Kern kern = p.is_bf16 ? attn_bwd_dkdv_kernel<D, true> : attn_bwd_dkdv_kernel<D, false>;
+  const size_t smem = sizeof(DkvSmem<D>) + 1024;
   cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
              "bwd_dkdv smem attr");
   const int items = p.batch * p.kv_heads * ((p.n_k + 127) / 128);

@@ -8,7 +8,7 @@
 //   warp 10     ring fetcher   : pulls the other ring ranks' K/V slots over NVLink with bulk-TMA copies
 //                                (peer global -> smem -> local global) and publishes per-owner ready counters;
 //                                also allocates / frees TMEM
-//   warp 11     PV issuer in the experimental split-half variant (RAB_FWD_SPLIT=1), idle otherwise
+//   warp 11     idle (keeps the warpgroup count at three for setmaxnreg)
 // (control warps sit on the highest warp ids: the warp scheduler favours them)
 //
 // TMEM (512 columns): S0 | S1 (128 fp32 columns each, P aliases the first 64 columns as packed 16-bit)
@@ -47,7 +47,6 @@ struct FwdSmem {
   uint64_t q_full[2], q_empty[2];
   uint64_t kv_full[NSLOT], kv_empty[NSLOT];
   uint64_t s_full[2], p_ready[2], o_done[2], epi_done[2];
-  uint64_t hs_full[2][2], hp_ready[2][2], hp_free[2][2];  // split-half variant: [q tile][logit half]
   uint64_t fetch_full[2];
   uint32_t tmem_base;
 };
@@ -281,146 +280,13 @@ __device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Split-half variant (experimental, RAB_FWD_SPLIT=1): the 128 logit columns of a tile are two independent 64-column
-// buffers per Q tile (columns [0,64) and [64,128) of its S region; P of a half is packed into the first 32 columns
-// of that half).  As soon as the warpgroup has turned the low half into P, warp 11 issues the K=64 half of P V and
-// warp 9 can refill the low buffer with the next tile's logits while the warpgroup is still busy with the high half:
-// the "next S cannot start before P V has consumed P" bubble of the one-buffer design disappears without changing the
-// K/V smem tiles, the TMA boxes or the tile scanner.  Cost: the S MMAs become N = 64 SS instructions (48 instead of 32
-// cycles each, shared-memory-operand bound, tools/mma_rate.py).
-// ------------------------------------------------------------------------------------------------
-template <int D, bool BF16>
-__device__ __forceinline__ void split_s_issuer(FwdSmem<D>& sm, const AttnFwdParams& p, uint32_t tmem_in) {
-  constexpr uint32_t idesc_qk = umma_idesc_bf16(BM, 64, 0, 0, BF16 ? 1 : 0);
-  constexpr uint64_t kmaj_static = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
-  constexpr uint32_t SLOT16 = FwdSmem<D>::TILE_BYTES >> 4;
-  constexpr uint32_t HALF16 = (64 * 128) >> 4;  // rows 64..127 of a K-major sub-tile start 8 KB in
-  const int lane = lane_id();
-  const uint32_t tmem = warp_uniform(tmem_in);
-  const uint64_t q_desc0 = umma_desc(kmaj_static, smem_u32(sm.q[0]));
-  const uint64_t q_desc1 = umma_desc(kmaj_static, smem_u32(sm.q[1]));
-  const uint64_t kv_kdesc0 = umma_desc(kmaj_static, smem_u32(sm.kv[0]));
-  uint32_t n_kv = 0;
-  uint32_t c_t[2] = {0, 0};      // tiles issued per Q tile (cumulative): hp_free parity
-  uint32_t items_t[2] = {0, 0};
-  const int total = num_items(p);
-  for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
-    Item it;
-    decode_item(p, idx, it);
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-      if (it.tvalid[t]) mbar_wait(&sm.q_full[t], items_t[t] & 1, 200 + t);
-    tc_fence_after();
-    FwdScan scan;
-    init_scan(scan, p, it);
-    ScanTile cur;
-    while (scan.next(lane, cur)) {
-      const uint32_t ks = (2 * n_kv) % NSLOT, kph = ((2 * n_kv) / NSLOT) & 1;
-      mbar_wait(&sm.kv_full[ks], kph, 210);
-      tc_fence_after();
-      const uint64_t kd = kv_kdesc0 + uint64_t(ks * SLOT16);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (!cur.need[t]) continue;
-        const uint64_t qd = t ? q_desc1 : q_desc0;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          if (c_t[t] > 0) mbar_wait(&sm.hp_free[t][hf], (c_t[t] - 1u) & 1, 270 + 2 * t + hf);
-          tc_fence_after();
-          const uint32_t st = tmem + t * 128 + hf * 64;
-          const uint64_t kh = kd + uint64_t(hf * HALF16);
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-              const uint32_t off = (kk / 4) * SUB_BYTES + (kk % 4) * 32;
-              umma_ss(st, umma_desc_add(qd, off), umma_desc_add(kh, off), idesc_qk, kk > 0);
-            }
-            umma_commit(&sm.hs_full[t][hf]);
-          }
-          __syncwarp();
-        }
-        c_t[t]++;
-      }
-      umma_commit_w(&sm.kv_empty[ks]);
-      n_kv++;
-    }
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      if (!it.tvalid[t]) continue;
-      umma_commit_w(&sm.q_empty[t]);
-      items_t[t]++;
-    }
-  }
-}
-
-template <int D, bool BF16>
-__device__ __forceinline__ void split_pv_issuer(FwdSmem<D>& sm, const AttnFwdParams& p, uint32_t tmem_in) {
-  constexpr uint32_t idesc_pv = umma_idesc_bf16(BM, D, 0, 1, BF16 ? 1 : 0);
-  constexpr uint64_t vmaj_static = umma_smem_desc_hi_lo(SUB_BYTES, 1024, UMMA_LAYOUT_SW128);
-  constexpr uint32_t SLOT16 = FwdSmem<D>::TILE_BYTES >> 4;
-  const int lane = lane_id();
-  const uint32_t tmem = warp_uniform(tmem_in);
-  const uint64_t kv_vdesc0 = umma_desc(vmaj_static, smem_u32(sm.kv[0]));
-  uint32_t n_kv = 0;
-  uint32_t c_t[2] = {0, 0};      // tiles issued per Q tile (cumulative): hp_ready parity
-  uint32_t items_t[2] = {0, 0};
-  const int total = num_items(p);
-  for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
-    Item it;
-    decode_item(p, idx, it);
-    FwdScan scan;
-    init_scan(scan, p, it);
-    ScanTile cur;
-    bool pv_started[2] = {false, false};
-    while (scan.next(lane, cur)) {
-      const uint32_t vs = (2 * n_kv + 1) % NSLOT, vph = ((2 * n_kv + 1) / NSLOT) & 1;
-      mbar_wait(&sm.kv_full[vs], vph, 220);
-      tc_fence_after();
-      const uint64_t vd = kv_vdesc0 + uint64_t(vs * SLOT16);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (!cur.need[t]) continue;
-        if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 230 + t);
-        const uint32_t ot = tmem + 256 + t * D;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          mbar_wait(&sm.hp_ready[t][hf], c_t[t] & 1, 240 + 2 * t + hf);
-          tc_fence_after();
-          const uint32_t pt = tmem + t * 128 + hf * 64;
-          const uint32_t acc0 = (pv_started[t] || hf > 0) ? 1u : 0u;
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              umma_ts(ot, pt + kk * 8, umma_desc_add(vd, (hf * 4 + kk) * 2048), idesc_pv, kk > 0 ? 1u : acc0);
-            }
-            umma_commit(&sm.hp_free[t][hf]);
-            if (hf == 1) umma_commit(&sm.o_done[t]);
-          }
-          __syncwarp();
-        }
-        pv_started[t] = true;
-        c_t[t]++;
-      }
-      umma_commit_w(&sm.kv_empty[vs]);
-      n_kv++;
-    }
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      if (!it.tvalid[t]) continue;
-      // an item without any visible tile still has to hand the accumulator slot over in order
-      if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 260 + t);
-      items_t[t]++;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // warp 2: ring fetcher (peer K/V slot -> local slot, 1/gridDim of every slot per CTA)
 // ------------------------------------------------------------------------------------------------
 template <int D>
 __device__ __forceinline__ void fetch_role(FwdSmem<D>& sm, const AttnFwdParams& p) {
   uint32_t fcount = 0;
   const unsigned long long npieces = (p.slot_bytes + FETCH_PIECE - 1) / FETCH_PIECE;
+  const unsigned long long t_begin = global_timer_ns();
   for (int s = 1; s < p.hop_count; ++s) {
     const int o = p.hop_owner[s];
     const uint8_t* src = p.kv_peer[o];  // owner o's own slot (peer-mapped staging)
@@ -461,6 +327,10 @@ __device__ __forceinline__ void fetch_role(FwdSmem<D>& sm, const AttnFwdParams& 
     __threadfence();
     red_release_gpu_add(&p.ready[o], 1u);
   }
+  if (p.fetch_times != nullptr && p.hop_count > 1) {  // bench.py: ring K/V GB/s over the fetch-active window
+    p.fetch_times[2 * blockIdx.x] = t_begin;
+    p.fetch_times[2 * blockIdx.x + 1] = global_timer_ns();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -489,7 +359,7 @@ __device__ __forceinline__ uint32_t scale_packed(uint32_t w, float f) {
 }
 
 // POLYQ of every 4 logit pairs take their exponential on the FMA pipe (poly_exp2x2) instead of the MUFU.
-template <int D, bool BF16, int POLYQ, bool SPLIT>
+template <int D, bool BF16, int POLYQ>
 __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams& p, const int t, uint32_t tmem) {
   const int wg_tid = threadIdx.x - 128 * t;
   const uint32_t lane_off = uint32_t((wg_tid / 32) * 32) << 16;
@@ -501,7 +371,6 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
   uint64_t* const o_done = &sm.o_done[0] + t;
   uint64_t* const epi_done = &sm.epi_done[0] + t;
   uint32_t cnt = 0;
-  uint32_t n_half[2] = {0, 0};  // split variant: halves handed to the PV issuer so far (cumulative)
 
   const bool clamp = p.softclamp > 0.f;
   const float mul = clamp ? 1.f : p.scale * kLog2e;
@@ -531,10 +400,8 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
       const bool need = t ? ti.need[1] : ti.need[0];
       if (!need) continue;
       const bool part = t ? ti.part[1] : ti.part[0];
-      if constexpr (!SPLIT) {
-        mbar_wait(s_full, cnt & 1, 400 + t);
-        tc_fence_after();
-      }
+      mbar_wait(s_full, cnt & 1, 400 + t);
+      tc_fence_after();
 
       // per-tile mask context (only used on partial tiles)
       const int c0 = ti.idx * BN;
@@ -586,13 +453,7 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
           ls01 = fmul2(ls01, make_float2(factor, factor));
           ls23 = fmul2(ls23, make_float2(factor, factor));
           if (have_o) {
-            // one-buffer variant: the previous P V of this tile completed before S became visible (commit ordering).
-            // split variant: S runs ahead of P V, so wait until every half handed over so far has been consumed.
-            if constexpr (SPLIT) {
-              if (n_half[0] > 0) mbar_wait(&sm.hp_free[t][0], (n_half[0] - 1u) & 1, 420 + t);
-              if (n_half[1] > 0) mbar_wait(&sm.hp_free[t][1], (n_half[1] - 1u) & 1, 422 + t);
-              tc_fence_after();
-            }
+            // the previous P V of this Q tile completed before S became visible (commit ordering)
 #pragma unroll 1
             for (int cc = 0; cc < D; cc += 32) {
               uint32_t orr[32];
@@ -604,8 +465,8 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
             }
           }
 #pragma unroll 1
-          for (int cc = SPLIT ? (c & ~1) : 0; cc < c; ++cc) {
-            const uint32_t pcol = SPLIT ? (cc >> 1) * 64 + (cc & 1) * 16 : cc * 16;
+          for (int cc = 0; cc < c; ++cc) {
+            const uint32_t pcol = cc * 16;
             uint32_t pw[16];
             tmem_ld16(s_tm + pcol, pw);
             tc_wait_ld();
@@ -631,30 +492,11 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
           w16[i] = BF16 ? pack_bf16x2(pa.x, pa.y) : pack_f16x2(pa.x, pa.y);
           w16[i + 1] = BF16 ? pack_bf16x2(pb.x, pb.y) : pack_f16x2(pb.x, pb.y);
         }
-        tmem_st16(s_tm + (SPLIT ? (c >> 1) * 64 + (c & 1) * 16 : c * 16), w16);
+        tmem_st16(s_tm + c * 16, w16);
       };
 
       uint32_t xa[32], xb[32];
-      if constexpr (SPLIT) {
-        // one iteration per 64-column half: wait for its logits, turn them into P, hand the half to the PV issuer
-#pragma unroll 1
-        for (int c = 0; c < 4; c += 2) {
-          const int hf = c >> 1;
-          mbar_wait(&sm.hs_full[t][hf], cnt & 1, 400 + 2 * t + hf);
-          tc_fence_after();
-          tmem_ld32(s_tm + c * 32, xa);
-          tc_wait_ld();
-          tmem_ld32(s_tm + (c + 1) * 32, xb);
-          process(xa, c);
-          tc_wait_ld();
-          process(xb, c + 1);
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(&sm.hp_ready[t][hf]);
-          n_half[hf]++;
-          have_o = true;
-        }
-      } else {
+      {
         tmem_ld32(s_tm, xa);
 #pragma unroll 1
         for (int c = 0; c < 4; c += 2) {
@@ -667,11 +509,9 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
         }
       }
       l += (ls01.x + ls01.y) + (ls23.x + ls23.y);
-      if constexpr (!SPLIT) {
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(p_ready);
-      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_ready);
       cnt++;
       cnt_item++;
       have_o = true;
@@ -715,7 +555,7 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
   }
 }
 
-template <int D, bool BF16, int POLYQ, bool SPLIT>
+template <int D, bool BF16, int POLYQ>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                 const __grid_constant__ AttnFwdParams p) {
@@ -733,11 +573,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_init(&sm.o_done[i], 1);
       mbar_init(&sm.epi_done[i], 128);
       mbar_init(&sm.fetch_full[i], 1);
-      for (int hf = 0; hf < 2; ++hf) {
-        mbar_init(&sm.hs_full[i][hf], 1);
-        mbar_init(&sm.hp_ready[i][hf], 128);
-        mbar_init(&sm.hp_free[i][hf], 1);
-      }
     }
     for (int i = 0; i < NSLOT; ++i) {
       mbar_init(&sm.kv_full[i], 1);
@@ -765,16 +600,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (warp == 8) {
       producer_role<D>(sm, p, &map_q, &map_kv);
     } else if (warp == 9) {
-      if constexpr (SPLIT) split_s_issuer<D, BF16>(sm, p, tmem);
-      else mma_role<D, BF16>(sm, p, tmem);
+      mma_role<D, BF16>(sm, p, tmem);
     } else if (warp == 10) {
       if (lane_id() == 0) fetch_role<D>(sm, p);
-    } else {
-      if constexpr (SPLIT) split_pv_issuer<D, BF16>(sm, p, tmem);
     }
   } else {
     setmaxnreg_inc<192>();
-    softmax_role<D, BF16, POLYQ, SPLIT>(sm, p, warp < 4 ? 0 : 1, tmem);
+    softmax_role<D, BF16, POLYQ>(sm, p, warp < 4 ? 0 : 1, tmem);
   }
 
   tc_fence_before();
@@ -798,18 +630,11 @@ void launch_attn_fwd(const CUtensorMap& map_q, const CUtensorMap& map_kv, const 
     const char* e = std::getenv("RAB_FWD_EXP_POLY");
     return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? int(e[0] - '0') : 1;
   }();
-  // RAB_FWD_SPLIT=1: experimental split-half variant (two 64-column logit buffers per Q tile, separate S and PV issuers);
-  // compiled and reviewed but NOT yet run on a GPU — off by default.
-  static const bool split = [] {
-    const char* e = std::getenv("RAB_FWD_SPLIT");
-    return e != nullptr && e[0] == '1';
-  }();
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const AttnFwdParams);
   Kern kern;
-  if (split) kern = p.is_bf16 ? attn_fwd_kernel<D, true, 1, true> : attn_fwd_kernel<D, false, 1, true>;
-  else if (polyq == 2) kern = p.is_bf16 ? attn_fwd_kernel<D, true, 2, false> : attn_fwd_kernel<D, false, 2, false>;
-  else if (polyq == 1) kern = p.is_bf16 ? attn_fwd_kernel<D, true, 1, false> : attn_fwd_kernel<D, false, 1, false>;
-  else kern = p.is_bf16 ? attn_fwd_kernel<D, true, 0, false> : attn_fwd_kernel<D, false, 0, false>;
+  if (polyq == 2) kern = p.is_bf16 ? attn_fwd_kernel<D, true, 2> : attn_fwd_kernel<D, false, 2>;
+  else if (polyq == 1) kern = p.is_bf16 ? attn_fwd_kernel<D, true, 1> : attn_fwd_kernel<D, false, 1>;
+  else kern = p.is_bf16 ? attn_fwd_kernel<D, true, 0> : attn_fwd_kernel<D, false, 0>;
   const size_t smem = sizeof(FwdSmem<D>) + 1024;
   cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
              "attn_fwd smem attribute");

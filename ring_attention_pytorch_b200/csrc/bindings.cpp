@@ -23,6 +23,21 @@ int sm_count() {
   return n;
 }
 
+// bench.py hook: when set, the next forward launches record the activity window of their in-kernel K/V fetchers
+unsigned long long* g_fetch_times = nullptr;
+int64_t g_fetch_times_rows = 0;
+
+void set_fetch_timing(const c10::optional<Tensor>& t) {
+  if (!t.has_value()) {
+    g_fetch_times = nullptr;
+    g_fetch_times_rows = 0;
+    return;
+  }
+  TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->is_contiguous() && t->dim() == 2 && t->size(1) == 2);
+  g_fetch_times = reinterpret_cast<unsigned long long*>(t->data_ptr<int64_t>());
+  g_fetch_times_rows = t->size(0);
+}
+
 void check_16bit(const Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
   TORCH_CHECK(t.scalar_type() == at::kBFloat16 || t.scalar_type() == at::kHalf, name, " must be bf16 or fp16");
@@ -155,6 +170,7 @@ std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& kv_buf, at::I
     p.kv_peer[i] = peer_ptrs[i] ? reinterpret_cast<const uint8_t*>(peer_ptrs[i]) : p.kv_local + i * p.slot_bytes;
   p.ready = reinterpret_cast<uint32_t*>(ready.data_ptr<int>());
   rab::cuda_check(cudaMemsetAsync(p.ready, 0, sizeof(uint32_t) * world, stream), "ready memset");
+  p.fetch_times = (g_fetch_times != nullptr && g_fetch_times_rows >= sm_count()) ? g_fetch_times : nullptr;
 
   // Q: [b, n, h, d] -> dims (d, h, n, b), box (64, 1, 128, 1)
   uint64_t qdims[4] = {(uint64_t)d, (uint64_t)h, (uint64_t)n_q, (uint64_t)b};
@@ -302,34 +318,112 @@ std::tuple<Tensor, Tensor> attn_bwd_dkdv(const Tensor& qdo_buf, const Tensor& kv
   return {dk, dv};
 }
 
-// Experimental one-kernel backward (single rank, D = 128): dK/dV as above, dQ accumulated into `dq_acc` (fp32
-// [b, n_q, h, d], zero-initialised by the caller) with red.global.add.f32.  See attn_bwd_sm100.cu, MODE 3.
-std::tuple<Tensor, Tensor> attn_bwd_fused(const Tensor& qdo_buf, const Tensor& kv_buf, const Tensor& stat_buf,
+// One-kernel (5-GEMM) ring backward, head dim 128 (attn_bwd_fused_sm100.cu).
+//   qdo [2][b*h][n_q][d] 16 bit and stat [2][b*h][n_pad] fp32: this rank's bwd_prep output
+//   kv_buf [world][2][b*hk][n_k][d]: the K/V gather (slot o valid once ready[o] >= ready_target; no flags: all valid)
+//   dq_acc fp32 [b*h][n_pad][d], zeroed by the caller: dQ (unscaled) is ADDED into it
+//   dkv_acc_ptrs: empty -> dK, dV are returned as 16 bit [b, n_k, hk, d] (single rank);
+//                 else one pointer per ring rank to that rank's zeroed fp32 [2][b*hk][nk_pad][d] accumulator (peer
+//                 mapped): the kernel adds its dK / dV tiles into the owner's accumulator and returns empty tensors
+std::tuple<Tensor, Tensor> attn_bwd_ring(const Tensor& qdo, const Tensor& kv_buf, const Tensor& stat, Tensor dq_acc,
                                          const c10::optional<Tensor>& ready, int64_t ready_target,
                                          const c10::optional<Tensor>& kmask_bits, int64_t batch, int64_t heads,
                                          int64_t kv_heads, int64_t rank, bool causal, int64_t window, double scale,
                                          double softclamp, int64_t pos_stride, int64_t seg_len, at::IntArrayRef base0,
-                                         at::IntArrayRef base1, int64_t q_pos_offset, at::IntArrayRef hop_owner, Tensor dq_acc) {
+                                         at::IntArrayRef base1, int64_t q_pos_offset, at::IntArrayRef hop_owner,
+                                         at::IntArrayRef dkv_acc_ptrs, int64_t nk_pad) {
+  check_16bit(qdo, "qdo");
+  check_16bit(kv_buf, "kv_buf");
+  TORCH_CHECK(qdo.is_contiguous() && kv_buf.is_contiguous() && stat.is_contiguous() && dq_acc.is_contiguous());
+  TORCH_CHECK(kv_buf.dim() == 5 && qdo.dim() == 4 && stat.dim() == 3 && dq_acc.dim() == 3);
+  const int world = kv_buf.size(0), n_k = kv_buf.size(3), d = kv_buf.size(4);
+  const int n_q = qdo.size(2), n_pad = stat.size(2);
+  TORCH_CHECK(d == 128, "attn_bwd_ring: head dim 128 only");
+  TORCH_CHECK(qdo.size(0) == 2 && qdo.size(1) == batch * heads && qdo.size(3) == d);
+  TORCH_CHECK(stat.size(0) == 2 && stat.size(1) == batch * heads && stat.scalar_type() == at::kFloat);
+  TORCH_CHECK(n_pad % 64 == 0 && n_pad >= n_q);
+  TORCH_CHECK(dq_acc.scalar_type() == at::kFloat && dq_acc.size(0) == batch * heads && dq_acc.size(1) == n_pad &&
+              dq_acc.size(2) == d);
+  TORCH_CHECK(kv_buf.size(1) == 2 && kv_buf.size(2) == batch * kv_heads && heads % kv_heads == 0);
+  TORCH_CHECK(world <= rab::kMaxWorld && hop_owner.size() >= 1 && (int)hop_owner.size() <= world &&
+              hop_owner[0] == rank);
   c10::cuda::CUDAGuard guard(kv_buf.device());
-  BwdSetup s = make_bwd_setup(qdo_buf, kv_buf, stat_buf, ready, ready_target, kmask_bits, batch, heads, kv_heads, rank,
-                              causal, window, scale, softclamp, pos_stride, seg_len, base0, base1, q_pos_offset,
-                              hop_owner);
-  const int d = kv_buf.size(4);
-  TORCH_CHECK(d == 128 && hop_owner.size() == 1, "attn_bwd_fused: head dim 128, single rank only");
-  TORCH_CHECK(dq_acc.scalar_type() == at::kFloat && dq_acc.is_contiguous() && dq_acc.is_cuda());
-  TORCH_CHECK(dq_acc.numel() == (int64_t)batch * s.p.n_q * heads * d, "dq_acc must be [b, n_q, h, d] fp32");
-  s.p.dq_acc = dq_acc.data_ptr<float>();
-  Tensor dk = torch::empty({batch, s.p.n_k, kv_heads, d}, kv_buf.options());
-  Tensor dv = torch::empty({batch, s.p.n_k, kv_heads, d}, kv_buf.options());
-  s.p.dk = dk.data_ptr();
-  s.p.dv = dv.data_ptr();
   auto stream = at::cuda::getCurrentCUDAStream();
-  if (d == 128) {
-    rab::launch_attn_bwd_dkdv<128>(s.map_qd64, s.map_kv, s.p, sm_count(), stream);
-  } else {
-    rab::launch_attn_bwd_dkdv<64>(s.map_qd64, s.map_kv, s.p, sm_count(), stream);
+
+  rab::AttnBwdFusedParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.batch = (int)batch; p.heads = (int)heads; p.kv_heads = (int)kv_heads;
+  p.n_q = n_q; p.n_k = n_k; p.n_pad = n_pad; p.nk_pad = (int)nk_pad;
+  p.world = world; p.rank = (int)rank;
+  p.causal = causal; p.window = (int)window;
+  p.is_bf16 = kv_buf.scalar_type() == at::kBFloat16;
+  p.scale = (float)scale; p.softclamp = (float)softclamp;
+  fill_posmap(p.pos, pos_stride, seg_len, base0, base1, world);
+  p.q_pos_offset = (int)q_pos_offset;
+  p.hop_count = (int)hop_owner.size();
+  for (int i = 0; i < p.hop_count; ++i) p.hop_owner[i] = (int)hop_owner[i];
+  p.self_owner[0] = (int)rank;
+  p.stat = stat.data_ptr<float>();
+  if (kmask_bits.has_value()) {
+    const Tensor& km = *kmask_bits;
+    TORCH_CHECK(km.is_cuda() && km.scalar_type() == at::kInt && km.is_contiguous() && km.dim() == 3);
+    TORCH_CHECK(km.size(0) == world && km.size(1) == batch && km.size(2) % 4 == 0 && km.size(2) * 32 >= n_k);
+    p.kmask_bits = reinterpret_cast<const uint32_t*>(km.data_ptr<int>());
+    p.kmask_words = km.size(2);
   }
+  if (ready.has_value()) {
+    TORCH_CHECK(ready->is_cuda() && ready->scalar_type() == at::kInt && ready->numel() >= world);
+    p.ready = reinterpret_cast<const uint32_t*>(ready->data_ptr<int>());
+    p.ready_target = (uint32_t)ready_target;
+  }
+  // local Q / dO: dims (d, n_q, b*h, 2), box (64, 64, 1, 1)
+  uint64_t qdims[4] = {(uint64_t)d, (uint64_t)n_q, (uint64_t)batch * heads, 2};
+  uint64_t qstr[3] = {(uint64_t)d * 2, (uint64_t)n_q * d * 2, (uint64_t)batch * heads * n_q * d * 2};
+  uint32_t qbox64[4] = {64, 64, 1, 1};
+  CUtensorMap map_qd64 = rab::make_tmap_bf16(qdo.data_ptr(), 4, qdims, qstr, qbox64, rab::TmapSwizzle::B128);
+  uint64_t kdims[4] = {(uint64_t)d, (uint64_t)n_k, (uint64_t)batch * kv_heads, (uint64_t)2 * world};
+  uint64_t kstr[3] = {(uint64_t)d * 2, (uint64_t)n_k * d * 2, (uint64_t)batch * kv_heads * n_k * d * 2};
+  uint32_t kbox[4] = {64, 128, 1, 1};
+  CUtensorMap map_kv = rab::make_tmap_bf16(kv_buf.data_ptr(), 4, kdims, kstr, kbox, rab::TmapSwizzle::B128);
+  // dQ accumulator: 2-D (d, b*h*n_pad) fp32, box 32 columns x 32 rows, no swizzle (rows written lane-contiguous)
+  uint64_t adims[2] = {(uint64_t)d, (uint64_t)batch * heads * n_pad};
+  uint64_t astr[1] = {(uint64_t)d * 4};
+  uint32_t abox[2] = {32, 32};
+  CUtensorMap map_dq = rab::make_tmap_f32(dq_acc.data_ptr(), 2, adims, astr, abox, rab::TmapSwizzle::None);
+
+  Tensor dk, dv;
+  if (dkv_acc_ptrs.empty()) {
+    dk = torch::empty({batch, n_k, kv_heads, d}, kv_buf.options());
+    dv = torch::empty({batch, n_k, kv_heads, d}, kv_buf.options());
+    p.dk = dk.data_ptr();
+    p.dv = dv.data_ptr();
+    p.ring_reduce = 0;
+  } else {
+    TORCH_CHECK((int)dkv_acc_ptrs.size() == world && nk_pad % 128 == 0 && nk_pad >= n_k);
+    dk = torch::empty({0}, kv_buf.options());
+    dv = torch::empty({0}, kv_buf.options());
+    p.ring_reduce = 1;
+    uint64_t ddims[2] = {(uint64_t)d, (uint64_t)2 * batch * kv_heads * nk_pad};
+    uint64_t dstr[1] = {(uint64_t)d * 4};
+    uint32_t dbox[2] = {32, 32};
+    for (int o = 0; o < world; ++o)
+      p.map_dkv[o] = rab::make_tmap_f32(reinterpret_cast<const void*>(dkv_acc_ptrs[o]), 2, ddims, dstr, dbox,
+                                        rab::TmapSwizzle::B128);
+  }
+  rab::launch_attn_bwd_fused(map_qd64, map_kv, map_dq, p, sm_count(), stream);
   return {dk, dv};
+}
+
+// acc fp32 [b*h][n_pad][d] -> out 16 bit [b][n][h][d] * scale
+void acc_convert(const Tensor& acc, Tensor out, double scale) {
+  TORCH_CHECK(acc.is_cuda() && acc.scalar_type() == at::kFloat && acc.is_contiguous() && acc.dim() == 3);
+  check_16bit(out, "out");
+  TORCH_CHECK(out.is_contiguous() && out.dim() == 4);
+  const int b = out.size(0), n = out.size(1), h = out.size(2), d = out.size(3);
+  TORCH_CHECK(acc.size(0) == b * h && acc.size(1) >= n && acc.size(2) == d && d % 8 == 0);
+  c10::cuda::CUDAGuard guard(acc.device());
+  rab::launch_acc_convert(acc.data_ptr<float>(), out.data_ptr(), b, h, n, (int)acc.size(1), d, (float)scale,
+                          out.scalar_type() == at::kBFloat16, at::cuda::getCurrentCUDAStream());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,6 +542,16 @@ void peer_copy(Tensor dst, int64_t src_ptr, int64_t nbytes) {
                   "peer_copy");
 }
 
+// Stream-ordered 32-bit flag write (cuStreamWriteValue32): a memory operation of the stream itself, no kernel and no
+// copy-engine job.  The backward uses it to publish "K/V slot o has landed" from the side stream while its persistent
+// kernel owns every SM (a flag written by a kernel could never be scheduled next to it).
+void stream_write_u32(Tensor flags, int64_t index, int64_t value) {
+  TORCH_CHECK(flags.is_cuda() && flags.scalar_type() == at::kInt && flags.is_contiguous() && index >= 0 &&
+              index < flags.numel());
+  c10::cuda::CUDAGuard guard(flags.device());
+  rab::stream_write_value32(flags.data_ptr<int>() + index, (uint32_t)value, at::cuda::getCurrentCUDAStream());
+}
+
 int64_t symm_open(const Tensor& handle) {
   TORCH_CHECK(!handle.is_cuda() && handle.scalar_type() == torch::kUInt8 && handle.numel() == rab::kIpcHandleBytes);
   return reinterpret_cast<int64_t>(rab::symm_open(handle.contiguous().data_ptr<uint8_t>()));
@@ -476,12 +580,15 @@ TORCH_LIBRARY(rab, m) {
         "kmask_bits, int batch, int heads, int kv_heads, int rank, bool causal, int window, float scale, float "
         "softclamp, int pos_stride, int seg_len, int[] base0, int[] base1, int q_pos_offset, int[] hop_owner) -> "
         "(Tensor, Tensor)");
-  m.def("attn_bwd_fused(Tensor qdo_buf, Tensor kv_buf, Tensor stat_buf, Tensor? ready, int ready_target, Tensor? "
-        "kmask_bits, int batch, int heads, int kv_heads, int rank, bool causal, int window, float scale, float "
-        "softclamp, int pos_stride, int seg_len, int[] base0, int[] base1, int q_pos_offset, int[] hop_owner, Tensor(a!) dq_acc) -> "
-        "(Tensor, Tensor)");
+  m.def("attn_bwd_ring(Tensor qdo, Tensor kv_buf, Tensor stat, Tensor(a!) dq_acc, Tensor? ready, int ready_target, "
+        "Tensor? kmask_bits, int batch, int heads, int kv_heads, int rank, bool causal, int window, float scale, float "
+        "softclamp, int pos_stride, int seg_len, int[] base0, int[] base1, int q_pos_offset, int[] hop_owner, int[] "
+        "dkv_acc_ptrs, int nk_pad) -> (Tensor, Tensor)");
+  m.def("acc_convert(Tensor acc, Tensor(a!) out, float scale) -> ()");
+  m.def("set_fetch_timing(Tensor? times) -> ()");
   m.def("device_barrier(int[] pad_ptrs, int rank, int epoch) -> ()");
   m.def("peer_copy(Tensor(a!) dst, int src_ptr, int nbytes) -> ()");
+  m.def("stream_write_u32(Tensor(a!) flags, int index, int value) -> ()");
   m.def("symm_alloc(int bytes) -> (Tensor, Tensor)");
   m.def("symm_open(Tensor handle) -> int");
   m.def("symm_close(int ptr) -> ()");
@@ -495,13 +602,16 @@ TORCH_LIBRARY_IMPL(rab, CUDA, m) {
   m.impl("bwd_prep", &bwd_prep);
   m.impl("attn_bwd_dq", &attn_bwd_dq);
   m.impl("attn_bwd_dkdv", &attn_bwd_dkdv);
-  m.impl("attn_bwd_fused", &attn_bwd_fused);
+  m.impl("attn_bwd_ring", &attn_bwd_ring);
+  m.impl("acc_convert", &acc_convert);
 }
 
 TORCH_LIBRARY_IMPL(rab, CompositeExplicitAutograd, m) {
   m.impl("umma_rate", &umma_rate);
+  m.impl("set_fetch_timing", &set_fetch_timing);
   m.impl("device_barrier", &device_barrier);
   m.impl("peer_copy", &peer_copy);
+  m.impl("stream_write_u32", &stream_write_u32);
   m.impl("tree_decode_reduce", &tree_decode_reduce);
   m.impl("symm_alloc", &symm_alloc);
   m.impl("symm_open", &symm_open);

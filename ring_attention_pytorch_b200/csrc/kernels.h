@@ -71,6 +71,7 @@ struct AttnFwdParams {
   const uint8_t* kv_peer[kMaxWorld];  // kv_peer[o]: owner o's own [2][b*hk][n_k][d] slot (peer-mapped)
   unsigned long long slot_bytes;      // bytes of one owner slot (K and V)
   uint32_t* ready;                    // [world] arrival counters, zero before launch
+  unsigned long long* fetch_times;    // optional [gridDim][2] globaltimer ns: first / last activity of each CTA's fetcher
 };
 
 template <int D>
@@ -105,7 +106,6 @@ struct AttnBwdParams {
   int kmask_words;
   const uint32_t* ready;       // [world] flags: slot o usable once ready[o] >= ready_target (may be null)
   uint32_t ready_target;
-  float* dq_acc;               // experimental one-kernel backward: fp32 [b, n_q, h, d] accumulator (null = off)
 };
 
 template <int D>
@@ -114,6 +114,41 @@ void launch_attn_bwd_dq(const CUtensorMap& map_qd, const CUtensorMap& map_kv, co
 template <int D>
 void launch_attn_bwd_dkdv(const CUtensorMap& map_qd64, const CUtensorMap& map_kv, const AttnBwdParams& p,
                           int num_sms, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// one-kernel (5-GEMM) ring backward, head dim 128 (attn_bwd_fused_sm100.cu)
+//   local  : qdo [2][b*h][n_q][d] 16 bit, stat [2][b*h][n_pad] fp32 (lse*log2e, delta), dq_acc fp32 [b*h][n_pad][d]
+//   K/V    : gather buffer [world][2][b*hk][n_k][d]; slot o usable once ready[o] >= ready_target (null: always)
+//   dK/dV  : ring_reduce == 0: 16 bit [b, n_k, hk, d] written directly (single rank)
+//            ring_reduce == 1: added into owner o's fp32 [2][b*hk][nk_pad][d] accumulator through map_dkv[o]
+// ------------------------------------------------------------------------------------------------
+struct AttnBwdFusedParams {
+  int batch, heads, kv_heads;
+  int n_q, n_k, n_pad, nk_pad;
+  int world, rank;
+  int causal, window, is_bf16;
+  float scale, softclamp;
+  PosMap pos;
+  int q_pos_offset;
+  int hop_count;
+  int hop_owner[kMaxWorld];  // K/V owners visited, hop 0 is this rank
+  int self_owner[1];         // = {rank}: the streamed queries are always local
+  const float* stat;
+  const uint32_t* kmask_bits;  // [world][batch][kmask_words]
+  int kmask_words;
+  const uint32_t* ready;
+  uint32_t ready_target;
+  void* dk;
+  void* dv;
+  int ring_reduce;
+  alignas(64) CUtensorMap map_dkv[kMaxWorld];
+};
+void launch_attn_bwd_fused(const CUtensorMap& map_qd64, const CUtensorMap& map_kv, const CUtensorMap& map_dq,
+                           const AttnBwdFusedParams& p, int num_sms, cudaStream_t stream);
+size_t attn_bwd_fused_smem_bytes();
+// fp32 accumulator [b*h][n_pad][d] -> 16 bit [b][n][h][d], multiplied by scale
+void launch_acc_convert(const float* acc, void* out, int batch, int heads, int n, int n_pad, int d, float scale,
+                        int is_bf16, cudaStream_t stream);
 
 // q, o, do: [b, n, h, d] contiguous 16 bit; lse: [b, h, n] fp32 (natural log).
 // Writes this rank's slot: qdo_slot [2][b*h][n][d] (q, do) and stat_slot [2][b*h][n_pad] (lse*log2e, delta).

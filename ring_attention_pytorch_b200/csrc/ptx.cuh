@@ -29,6 +29,12 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

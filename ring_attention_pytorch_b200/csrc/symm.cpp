@@ -6,6 +6,9 @@
 // this file is transport-agnostic.
 #include "symm.h"
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -56,6 +59,23 @@ void* symm_open(const unsigned char handle[kIpcHandleBytes]) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_imports[p]++;
   return p;
+}
+
+void stream_write_value32(void* addr, unsigned int value, cudaStream_t stream) {
+  static PFN_cuStreamWriteValue32_v11070 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr)
+      throw std::runtime_error("[ring_attention_b200] cannot resolve cuStreamWriteValue32");
+    fn = reinterpret_cast<PFN_cuStreamWriteValue32_v11070>(p);
+  });
+  CUresult r = fn(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(addr), value,
+                  CU_STREAM_WRITE_VALUE_DEFAULT);
+  if (r != CUDA_SUCCESS)
+    throw std::runtime_error("[ring_attention_b200] cuStreamWriteValue32 failed with code " + std::to_string((int)r));
 }
 
 void symm_close(void* p) {

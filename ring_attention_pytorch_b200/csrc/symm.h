@@ -13,4 +13,8 @@ void symm_free(void* base);
 void* symm_open(const unsigned char handle[kIpcHandleBytes]);
 void symm_close(void* p);
 
+// cuStreamWriteValue32 on `stream` (resolved through the runtime, like the tensor-map encoder): *addr = value in
+// stream order, performed by the stream front end — no kernel, no copy engine.
+void stream_write_value32(void* addr, unsigned int value, cudaStream_t stream);
+
 }  // namespace rab

@@ -23,8 +23,9 @@ PFN_cuTensorMapEncodeTiled_v12000 resolve_encode() {
 }
 }  // namespace
 
-CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                           const uint32_t* box, TmapSwizzle swizzle) {
+namespace {
+CUtensorMap make_tmap_typed(CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box, TmapSwizzle swizzle) {
   auto encode = resolve_encode();
   CUtensorMap map;
   cuuint64_t gdims[5];
@@ -37,7 +38,7 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
     estr[i] = 1;
     if (i + 1 < rank) gstrides[i] = strides_bytes[i];
   }
-  CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims,
+  CUresult r = encode(&map, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdims,
                       gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       swizzle == TmapSwizzle::B128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -46,6 +47,17 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
                              std::to_string((int)r));
   }
   return map;
+}
+}  // namespace
+
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, TmapSwizzle swizzle) {
+  return make_tmap_typed(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle);
+}
+
+CUtensorMap make_tmap_f32(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box, TmapSwizzle swizzle) {
+  return make_tmap_typed(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle);
 }
 
 }  // namespace rab

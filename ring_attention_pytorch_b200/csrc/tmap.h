@@ -17,6 +17,10 @@ enum class TmapSwizzle { None = 0, B128 = 3 };
 CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                            const uint32_t* box, TmapSwizzle swizzle);
 
+// same for fp32 elements (accumulators that are the target of cp.reduce.async.bulk.tensor .add)
+CUtensorMap make_tmap_f32(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box, TmapSwizzle swizzle);
+
 inline void cuda_check(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {
     throw std::runtime_error(std::string("[ring_attention_b200] ") + what + ": " + cudaGetErrorString(e));

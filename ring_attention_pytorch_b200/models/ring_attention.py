@@ -39,6 +39,17 @@ from ring_attention_pytorch_b200.parallel.distributed import (
 from ring_attention_pytorch_b200.parallel.layout import make_position_map
 
 
+def sm100_kernels_usable(dim_head: int = 64) -> bool:
+    """Default of ``use_cuda_kernel``: the hand-written kernels are sm_100a only and cover head dims up to 128; on any
+    other GPU (or larger heads) the modules fall back to the portable ring op instead of failing at launch."""
+    if not torch.cuda.is_available() or dim_head > 128:
+        return False
+    try:
+        return torch.cuda.get_device_capability()[0] == 10
+    except Exception:  # noqa: BLE001
+        return False
+
+
 def cast_tuple(t, length: int = 1):
     return t if isinstance(t, tuple) else ((t,) * length)
 
@@ -242,7 +253,7 @@ class RingAttention(Module):
         use_cuda_kernel: Optional[bool] = None,
     ):
         super().__init__()
-        use_cuda_kernel = default(use_cuda_kernel, torch.cuda.is_available())
+        use_cuda_kernel = default(use_cuda_kernel, sm100_kernels_usable(dim_head))
         assert not (use_cuda_kernel and not torch.cuda.is_available())
         self.use_cuda_kernel = use_cuda_kernel
 
@@ -366,7 +377,7 @@ class RingTransformer(Module):
         ff_chunk_size: Optional[int] = None,
     ):
         super().__init__()
-        use_cuda_kernel = default(use_cuda_kernel, torch.cuda.is_available())
+        use_cuda_kernel = default(use_cuda_kernel, sm100_kernels_usable(dim_head))
         self.use_cuda_kernel = use_cuda_kernel
         assert not (use_cuda_kernel and not torch.cuda.is_available())
 
@@ -414,20 +425,26 @@ class RingTransformer(Module):
         use_ring = self.ring_attn and is_distributed() and not force_ring_reduce_off
 
         return_loss = return_loss or exists(labels)
+        label_mask = None
         if return_loss and not exists(labels):
+            # label i is token i + 1: its validity is the mask of token i + 1 (reference ring_attention.py:614 uses
+            # mask[:, 1:] as well); the input mask loses its last position together with the input
             x, labels = x[:, :-1], x[:, 1:]
             if exists(mask):
+                label_mask = mask[:, 1:]
                 mask = mask[:, :-1]
+        elif exists(labels) and exists(mask):
+            label_mask = mask[:, : labels.shape[1]]
 
         ring_size = default(ring_size, get_world_size())
 
         if auto_shard_seq:
             x, mask = maybe_pad_seq_and_mask(x, mask, self.ring_seq_size)
             if exists(labels):
-                label_mask = mask[:, : labels.shape[1]] if exists(mask) else None
                 labels, label_mask = maybe_pad_seq_and_mask(labels, label_mask, self.ring_seq_size)
                 if exists(label_mask):
                     labels = labels.masked_fill(~label_mask, self.ignore_index)
+                    label_mask = None
             if self.striped_ring_attn:
                 x = stripe(x, self.ring_seq_size)
                 if exists(labels):
@@ -438,6 +455,9 @@ class RingTransformer(Module):
             if exists(labels):
                 (labels, _), *_ = sharded_batch_to_sharded_seq(labels, None, self.ring_seq_size)
             ring_size = get_world_size() // num_sharded_batches
+
+        if exists(labels) and exists(label_mask):  # not auto-sharded: padded targets are ignored as well
+            labels = labels.masked_fill(~label_mask, self.ignore_index)
 
         n = x.shape[-1]
         if use_ring:

@@ -142,32 +142,50 @@ def fused_attn_bwd(
     return dq, dk, dv
 
 
-def fused_attn_bwd_one_kernel(
-    qdo_buf: torch.Tensor,
+def pad128(n: int) -> int:
+    return (n + 127) // 128 * 128
+
+
+def fused_attn_bwd_ring(
+    qdo: torch.Tensor,
+    stat: torch.Tensor,
     kv_buf: torch.Tensor,
-    stat_buf: torch.Tensor,
     kmask_bits: Optional[torch.Tensor],
     *,
     batch: int,
     heads: int,
     kv_heads: int,
-    n_q: int,
+    rank: int,
     pm: PositionMap,
     causal: bool,
     window: Optional[int],
     scale: float,
     softclamp: float = 0.0,
     q_pos_offset: int = 0,
+    dq_acc: Optional[torch.Tensor] = None,
+    dkv_acc_ptrs: Sequence[int] = (),
+    nk_pad: int = 0,
+    ready: Optional[torch.Tensor] = None,
+    ready_target: int = 0,
+    hop_owner: Optional[List[int]] = None,
 ):
-    """EXPERIMENTAL (compile-checked, not yet validated on a GPU): the whole backward in the KV-stationary kernel — S and
-    dP are computed once (5 GEMMs instead of 7), dQ^T = K^T dS^T is reduced into an fp32 accumulator with
-    ``red.global.add.f32``.  Single rank, head dim 128 only.  Returns (dq fp32 [b, n_q, h, d], dk, dv)."""
+    """The one-kernel (5-GEMM) backward, head dim 128 (``csrc/attn_bwd_fused_sm100.cu``).
+
+    ``qdo`` [2, b*h, n_q, d] / ``stat`` [2, b*h, n_pad] are this rank's ``bwd_prep`` output, ``kv_buf`` the K/V gather.
+    dQ (unscaled) is added into ``dq_acc`` (fp32 [b*h, n_pad, d], allocated zeroed when not given).  Without
+    ``dkv_acc_ptrs`` dK / dV come back as 16-bit tensors; with them (one fp32 [2, b*hk, nk_pad, d] accumulator address
+    per ring rank) the kernel adds its tiles into the owners' accumulators and returns empty tensors.
+    Returns (dq_acc, dk, dv)."""
     ops = _ext.ops()
     d = kv_buf.shape[-1]
-    dq_acc = torch.zeros(batch, n_q, heads, d, dtype=torch.float32, device=kv_buf.device)
-    dk, dv = ops.attn_bwd_fused(qdo_buf, kv_buf, stat_buf, None, 0, kmask_bits, batch, heads, kv_heads, 0, bool(causal),
-                                int(window or 0), float(scale), float(softclamp), pm.stride, pm.seg_len, pm.base0,
-                                pm.base1, int(q_pos_offset), [0], dq_acc)
+    if dq_acc is None:
+        dq_acc = torch.zeros(batch * heads, stat.shape[-1], d, dtype=torch.float32, device=kv_buf.device)
+    if hop_owner is None:
+        hop_owner = ring_hop_owners(pm, rank, causal, window)
+    dk, dv = ops.attn_bwd_ring(qdo, kv_buf, stat, dq_acc, ready, int(ready_target), kmask_bits, batch, heads, kv_heads,
+                               rank, bool(causal), int(window or 0), float(scale), float(softclamp), pm.stride,
+                               pm.seg_len, pm.base0, pm.base1, int(q_pos_offset), list(hop_owner),
+                               list(dkv_acc_ptrs), int(nk_pad))
     return dq_acc, dk, dv
 
 
@@ -179,8 +197,12 @@ def emulate_ring_backward(
     softclamp: float = 0.0,
     key_masks=None,
     scale: Optional[float] = None,
+    fused: Optional[bool] = None,
 ):
-    """Backward of :func:`emulate_ring_forward` for every emulated rank on the current device."""
+    """Backward of :func:`emulate_ring_forward` for every emulated rank on the current device.
+
+    ``fused`` (default: head dim 128) selects the one-kernel backward: every emulated rank adds its dK / dV tiles into
+    the owners' fp32 accumulators, exactly what the ranks of a real ring do over NVLink."""
     ops = _ext.ops()
     world = len(qs)
     b, n, h, d = qs[0].shape
@@ -198,7 +220,33 @@ def emulate_ring_backward(
     kbits = None
     if key_masks is not None:
         kbits = pack_key_mask_bits(torch.stack(list(key_masks), 0))
+    if fused is None:
+        fused = d == 128
     res = []
+    if fused:
+        nk_pad = pad128(n)
+        ring = world > 1
+        accs = [torch.zeros(2, b * hk, nk_pad, d, dtype=torch.float32, device=dev) for _ in range(world)] if ring else []
+        ptrs = [a.data_ptr() for a in accs]
+        dqs, direct = [], []
+        for r in range(world):
+            dq_acc, dk, dv = fused_attn_bwd_ring(qdo_all[r], stat_all[r], kv_all, kbits, batch=b, heads=h, kv_heads=hk,
+                                                 rank=r, pm=pm, causal=causal, window=window, scale=scale,
+                                                 softclamp=softclamp, dkv_acc_ptrs=ptrs, nk_pad=nk_pad)
+            dqs.append(dq_acc)
+            direct.append((dk, dv))
+        for r in range(world):
+            dq = torch.empty(b, n, h, d, dtype=dt, device=dev)
+            ops.acc_convert(dqs[r], dq, scale)
+            if ring:
+                dk = torch.empty(b, n, hk, d, dtype=dt, device=dev)
+                dv = torch.empty_like(dk)
+                ops.acc_convert(accs[r][0], dk, 1.0)
+                ops.acc_convert(accs[r][1], dv, 1.0)
+            else:
+                dk, dv = direct[r]
+            res.append((dq, dk, dv))
+        return res
     for r in range(world):
         # every emulated rank sees the same fully gathered buffers (what the NVLink gather produces)
         res.append(fused_attn_bwd(qdo_all, kv_all, stat_all, kbits, batch=b, heads=h, kv_heads=hk, rank=r, pm=pm,

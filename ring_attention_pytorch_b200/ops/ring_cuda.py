@@ -5,13 +5,22 @@ Public surface mirrors reference ring_flash_attention_cuda.py:353-371 (``ring_fl
 
 Forward, per rank (one stream, no host synchronisation, no NCCL on the hot path):
 
-    pack_kv (K,V -> head-major slot) -> copy to symmetric staging -> device barrier ->
-    ONE fused kernel: tcgen05 flash attention over every hop of the ring while its fetcher warps pull
-    the other ranks' K/V slots over NVLink (bulk TMA) into the local gather buffer
+    pack_kv (K,V -> head-major) straight into this rank's slot of the SYMMETRIC gather workspace -> device barrier ->
+    ONE fused kernel: tcgen05 flash attention over every hop of the ring while its fetcher warps pull the other
+    ranks' K/V slots over NVLink (bulk TMA) into the local gather buffer
 
-Backward: ``bwd_prep`` (delta, lse->log2, Q/dO head-major) -> staging -> barrier -> copy engines pull the
-peers' Q/dO/stat slots on a side stream *while* the dQ kernel (which only needs the K/V gather saved by
-the forward) runs -> dK/dV kernel.  Every rank finishes its own dQ, dK, dV: no reduction, no atomics.
+Only q, k, v, o and the log-sum-exp are saved for the backward (O(n / W) activation memory per layer; the reference
+saves the same, ring_flash_attention_cuda.py:188-198).  The gather workspace is transient and shared by all layers.
+
+Backward, head dim 128 (``CONFIG["backward"] = "fused"``):
+
+    bwd_prep (delta, lse -> log2, Q/dO head-major) -> pack_kv into the gather workspace, zero the fp32 accumulators
+    -> device barrier -> [copy engines re-pull the peers' K/V slots on a side stream and publish per-owner flags] ->
+    ONE kernel: 5 GEMMs per tile pair, dQ added into a local fp32 accumulator (TMA reduction), dK/dV tiles added into
+    their OWNER's fp32 accumulators over NVLink from the kernel's epilogue -> device barrier -> fp32 -> 16 bit
+
+Head dim 64 (or ``CONFIG["backward"] = "two_kernel"``): dQ kernel + dK/dV kernel (7 GEMMs, no atomics, deterministic),
+the peers' Q / dO / statistics pulled by the copy engines while the dQ kernel runs.
 """
 from __future__ import annotations
 
@@ -28,25 +37,23 @@ from ring_attention_pytorch_b200.ops.fused import (
     alloc_kv_buffer,
     alloc_qdo_buffer,
     alloc_stat_buffer,
-    fused_attn_bwd,
+    fused_attn_bwd_ring,
     fused_attn_fwd,
     pack_key_mask_bits,
+    pad128,
 )
 from ring_attention_pytorch_b200.parallel.distributed import default, exists, get_rank, get_world_size, is_distributed
 from ring_attention_pytorch_b200.parallel.layout import make_position_map, ring_hop_owners, ring_query_owners
 from ring_attention_pytorch_b200.parallel.symm import get_workspace
+from ring_attention_pytorch_b200.utils.timing import nvtx_range
 
 # counts launches of our own kernels (bench.py reports it as gpu_launches)
 LAUNCHES = {"count": 0}
 
-# save_kv_gather=True : the forward's gathered K/V ([W, 2, b*hk, n, d], i.e. the whole ring's K/V) is kept for the
-#                       backward, whose dQ kernel then needs no communication at all (fastest).
-# save_kv_gather=False: only this rank's K/V slot is kept (O(n) activation memory per layer, the classic ring
-#                       attention footprint); the backward re-pulls the peers' slots with the copy engines before
-#                       the dQ kernel starts.
-# fused_backward=True  : EXPERIMENTAL, not yet validated on a GPU — single-rank, head-dim-128 calls run the whole
-#                        backward in one KV-stationary kernel (5 GEMMs, dQ through fp32 global reductions).
-CONFIG = {"save_kv_gather": True, "fused_backward": False}
+# backward="fused"     : head dim 128 runs the whole backward in ONE KV-stationary kernel (5 GEMMs; dQ through fp32 TMA
+#                        reductions, dK/dV added into the owner's accumulators over NVLink).
+# backward="two_kernel": the dQ + dK/dV kernel pair (7 GEMMs, no atomics, deterministic); head dim 64 always uses it.
+CONFIG = {"backward": "fused"}
 
 
 def _count(n: int = 1) -> None:
@@ -65,6 +72,16 @@ def _gather_ring_masks(mask: Tensor, ring_size: int) -> Tensor:
     dist.all_gather(gathered, mask.to(torch.uint8).contiguous())
     ring_set = get_rank() // ring_size
     return torch.stack(gathered[ring_set * ring_size:(ring_set + 1) * ring_size]).bool()
+
+
+def _ring_gather_workspace(ws, ring_size, b, hk, n_k, d_pad, dt):
+    """This call's K/V gather buffer ``[W, 2, b*hk, n_k, d]`` inside the symmetric workspace (double buffered across
+    calls) and, per ring rank, the address of THAT rank's own slot in ITS buffer (what the fetchers pull from)."""
+    slot_bytes = 2 * b * hk * n_k * d_pad * 2
+    local, bases = ws.staging("kv_gather", ring_size * slot_bytes)
+    gather = local[:ring_size * slot_bytes].view(dt).view(ring_size, 2, b * hk, n_k, d_pad)
+    own_slot_ptrs = [bases[o] + o * slot_bytes for o in range(ring_size)]
+    return gather, own_slot_ptrs, slot_bytes
 
 
 class RingFlashAttentionCUDAFunction(Function):
@@ -116,35 +133,38 @@ class RingFlashAttentionCUDAFunction(Function):
         q_off = (n_k - n_q) if (cross_attn and causal) else 0
         dev = q.device
 
-        kv_gather = alloc_kv_buffer(ring_size, b, hk, n_k, d_pad, dt, dev)
-        ops.pack_kv(kp, vp, kv_gather[rank])
-        _count()
         ready = torch.zeros(ring_size, dtype=torch.int32, device=dev)
         peers = [0] * ring_size
         kbits = None
-        if use_ring:
-            ws = get_workspace(ring_size, dev)
-            slot_bytes = kv_gather[rank].numel() * kv_gather.element_size()
-            stage, peer_ptrs = ws.staging(f"kv", slot_bytes)
-            stage.copy_(kv_gather[rank].view(torch.uint8).reshape(-1))
-            ws.barrier()
-            _count(2)
-            peers = [0 if o == rank else peer_ptrs[o] for o in range(ring_size)]
-            if exists(mask):
-                kbits = pack_key_mask_bits(_gather_ring_masks(mask, ring_size))
-        elif exists(mask):
-            kbits = pack_key_mask_bits(mask[None])
+        with nvtx_range("rab.fwd.pack+barrier"):
+            if use_ring:
+                ws = get_workspace(ring_size, dev)
+                kv_gather, own_slot_ptrs, _ = _ring_gather_workspace(ws, ring_size, b, hk, n_k, d_pad, dt)
+                ops.pack_kv(kp, vp, kv_gather[rank])
+                ws.barrier()  # every peer's own slot is complete
+                _count(2)
+                peers = [0 if o == rank else own_slot_ptrs[o] for o in range(ring_size)]
+                if exists(mask):
+                    kbits = pack_key_mask_bits(_gather_ring_masks(mask, ring_size))
+            else:
+                kv_gather = alloc_kv_buffer(1, b, hk, n_k, d_pad, dt, dev)
+                ops.pack_kv(kp, vp, kv_gather[0])
+                _count()
+                if exists(mask):
+                    kbits = pack_key_mask_bits(mask[None])
 
         softclamp = float(softclamp_value) if softclamp_qk_sim else 0.0
-        o, lse = fused_attn_fwd(qp, kv_gather, peers, ready, kbits, kv_heads=hk, rank=rank, pm=pm, causal=causal,
-                                window=max_lookback_seq_len, scale=scale, softclamp=softclamp, q_pos_offset=q_off)
+        with nvtx_range("rab.fwd.kernel"):
+            o, lse = fused_attn_fwd(qp, kv_gather, peers, ready, kbits, kv_heads=hk, rank=rank, pm=pm, causal=causal,
+                                    window=max_lookback_seq_len, scale=scale, softclamp=softclamp, q_pos_offset=q_off)
         _count()
 
-        keep_gather = CONFIG["save_kv_gather"] or not use_ring
         ctx.cfg = (causal, max_lookback_seq_len, ring_size, rank, layout, softclamp, scale, q_off, use_ring, d, d_pad,
-                   orig_dtype, hk, keep_gather)
-        kv_saved = kv_gather if keep_gather else kv_gather[rank].clone()
-        ctx.save_for_backward(qp, o, lse, kv_saved, kbits if kbits is not None else torch.empty(0, device=dev))
+                   orig_dtype, hk)
+        # single rank: the packed K/V is exactly what the backward needs; ring: keep the (small) inputs, re-pack later
+        none = torch.empty(0, device=dev)
+        ctx.save_for_backward(qp, kp if use_ring else none, vp if use_ring else none, o, lse,
+                              none if use_ring else kv_gather, kbits if kbits is not None else none)
         out = o[..., :d]
         return out.to(orig_dtype) if orig_dtype != dt else out
 
@@ -152,87 +172,118 @@ class RingFlashAttentionCUDAFunction(Function):
     def backward(ctx, do: Tensor):
         ops = _ext.ops()
         (causal, window, ring_size, rank, layout, softclamp, scale, q_off, use_ring, d, d_pad, orig_dtype,
-         hk, keep_gather) = ctx.cfg
-        qp, o, lse, kv_saved, kbits = ctx.saved_tensors
+         hk) = ctx.cfg
+        qp, kp, vp, o, lse, kv_saved, kbits = ctx.saved_tensors
         kbits = kbits if kbits.numel() > 0 else None
         dt = qp.dtype
         b, n_q, h, _ = qp.shape
         dev = qp.device
-        if keep_gather:
-            kv_gather = kv_saved
-        else:  # memory-lean mode: rebuild the gather buffer around this rank's own slot
-            kv_gather = alloc_kv_buffer(ring_size, b, hk, kv_saved.shape[2], d_pad, dt, dev)
-            kv_gather[rank].copy_(kv_saved)
-        n_k = kv_gather.shape[3]
-        pm = make_position_map(layout, ring_size, n_k)
         dop = _pad_head_dim(do.to(dt), d_pad).contiguous()
+        n_k = kp.shape[1] if use_ring else kv_saved.shape[3]
+        pm = make_position_map(layout, ring_size, n_k)
+        hop_owner = ring_hop_owners(pm, rank, causal, window)
 
-        qdo_gather = alloc_qdo_buffer(ring_size, b, h, n_q, d_pad, dt, dev)
-        stat_gather = alloc_stat_buffer(ring_size, b, h, n_q, dev)
-        ops.bwd_prep(qp, o, dop, lse, qdo_gather, stat_gather, rank)
-        _count()
-
-        gather_done = None
-        kv_done = None
-        if use_ring:
+        ws = None
+        kv_own_ptrs, kv_bytes = None, 0
+        if use_ring:  # rebuild the gather buffer around this rank's own slot (the forward's buffer is long reused)
             ws = get_workspace(ring_size, dev)
-            qdo_bytes = qdo_gather[rank].numel() * qdo_gather.element_size()
-            stat_bytes = stat_gather[rank].numel() * 4
-            stage, peer_ptrs = ws.staging("qdo", qdo_bytes + stat_bytes)
-            stage[:qdo_bytes].copy_(qdo_gather[rank].view(torch.uint8).reshape(-1))
-            stage[qdo_bytes:qdo_bytes + stat_bytes].copy_(stat_gather[rank].view(torch.uint8).reshape(-1))
-            kv_peer_ptrs = None
-            if not keep_gather:
-                kv_bytes = kv_gather[rank].numel() * kv_gather.element_size()
-                kv_stage, kv_peer_ptrs = ws.staging("kv", kv_bytes)
-                kv_stage.copy_(kv_gather[rank].view(torch.uint8).reshape(-1))
-            ws.barrier()
-            _count(3)
+            kv_gather, kv_own_ptrs, kv_bytes = _ring_gather_workspace(ws, ring_size, b, hk, n_k, d_pad, dt)
+            ops.pack_kv(kp, vp, kv_gather[rank])
+            _count()
+        else:
+            kv_gather = kv_saved
+
+        def pull_kv_slots():
+            """Side stream: copy engines pull the peers' K/V slots and publish one stream-ordered flag per owner, so the
+            backward kernel's hop 0 (local K/V) overlaps with the transfer.  Call after the device barrier."""
+            ready = torch.zeros(ring_size, dtype=torch.int32, device=dev)
             main = torch.cuda.current_stream(dev)
             start = torch.cuda.Event()
             start.record(main)
-            q_owners = ring_query_owners(pm, rank, causal, window)
             with torch.cuda.stream(ws.side_stream):
                 ws.side_stream.wait_event(start)
-                if kv_peer_ptrs is not None:  # K/V first: the dQ kernel is waiting for it
-                    for o_rank in ring_hop_owners(pm, rank, causal, window)[1:]:
-                        ops.peer_copy(kv_gather[o_rank], kv_peer_ptrs[o_rank], kv_bytes)
-                    kv_done = torch.cuda.Event()
-                    kv_done.record(ws.side_stream)
-                    kv_gather.record_stream(ws.side_stream)
-                for o_rank in q_owners[1:]:
-                    ops.peer_copy(qdo_gather[o_rank], peer_ptrs[o_rank], qdo_bytes)
-                    ops.peer_copy(stat_gather[o_rank], peer_ptrs[o_rank] + qdo_bytes, stat_bytes)
-                gather_done = torch.cuda.Event()
-                gather_done.record(ws.side_stream)
-            qdo_gather.record_stream(ws.side_stream)
-            stat_gather.record_stream(ws.side_stream)
+                for o_rank in hop_owner[1:]:
+                    ops.peer_copy(kv_gather[o_rank], kv_own_ptrs[o_rank], kv_bytes)
+                    ops.stream_write_u32(ready, o_rank, 1)  # stream memory op: needs no SM (the kernel owns them all)
+                done = torch.cuda.Event()
+                done.record(ws.side_stream)
+            ready.record_stream(ws.side_stream)
+            return ready, done
 
-        if CONFIG["fused_backward"] and not use_ring and d_pad == 128:
-            from ring_attention_pytorch_b200.ops.fused import fused_attn_bwd_one_kernel
-
-            dq32, dk, dv = fused_attn_bwd_one_kernel(qdo_gather, kv_gather, stat_gather, kbits, batch=b, heads=h,
-                                                     kv_heads=hk, n_q=n_q, pm=pm, causal=causal, window=window,
-                                                     scale=scale, softclamp=softclamp, q_pos_offset=q_off)
-            _count(1)
-            dq = dq32.to(dt)
-            dq, dk, dv = dq[..., :d], dk[..., :d], dv[..., :d]
-            if orig_dtype != dt:
-                dq, dk, dv = dq.to(orig_dtype), dk.to(orig_dtype), dv.to(orig_dtype)
-            return dq, dk, dv, None, None, None, None, None, None, None, None, None, None
-
-        common = (kbits, b, h, hk, rank, bool(causal), int(window or 0), float(scale), float(softclamp), pm.stride,
-                  pm.seg_len, pm.base0, pm.base1, int(q_off))
-        # dQ only needs the K/V gather (saved by the forward, or just re-pulled): it overlaps with the Q/dO gather
-        if kv_done is not None:
-            torch.cuda.current_stream(dev).wait_event(kv_done)
-        dq = ops.attn_bwd_dq(qdo_gather, kv_gather, stat_gather, None, 0, *common,
-                             ring_hop_owners(pm, rank, causal, window))
-        if gather_done is not None:
-            torch.cuda.current_stream(dev).wait_event(gather_done)
-        dk, dv = ops.attn_bwd_dkdv(qdo_gather, kv_gather, stat_gather, None, 0, *common,
-                                   ring_query_owners(pm, rank, causal, window))
-        _count(2)
+        if d_pad == 128 and CONFIG["backward"] == "fused":
+            # ---------------- one-kernel backward (csrc/attn_bwd_fused_sm100.cu) ----------------
+            with nvtx_range("rab.bwd.prep"):
+                qdo = alloc_qdo_buffer(1, b, h, n_q, d_pad, dt, dev)
+                stat = alloc_stat_buffer(1, b, h, n_q, dev)
+                ops.bwd_prep(qp, o, dop, lse, qdo, stat, 0)
+                dq_acc = torch.zeros(b * h, stat.shape[-1], d_pad, dtype=torch.float32, device=dev)
+                _count(2)
+            ready, ready_target, side_done, acc, acc_ptrs, nk_pad = None, 0, None, None, (), 0
+            if use_ring:
+                with nvtx_range("rab.bwd.zero+barrier"):
+                    nk_pad = pad128(n_k)
+                    acc_bytes = 2 * b * hk * nk_pad * d_pad * 4
+                    region = ws.region("dkv_acc", acc_bytes)
+                    acc = region.local[:acc_bytes].view(torch.float32).view(2, b * hk, nk_pad, d_pad)
+                    acc.zero_()
+                    acc_ptrs = region.peer_ptrs
+                    ws.barrier()  # every peer's accumulators are zero and its own K/V slot is complete
+                    _count(2)
+                    ready, side_done = pull_kv_slots()
+                    ready_target = 1
+            with nvtx_range("rab.bwd.kernel"):
+                _, dk, dv = fused_attn_bwd_ring(qdo[0], stat[0], kv_gather, kbits, batch=b, heads=h, kv_heads=hk,
+                                                rank=rank, pm=pm, causal=causal, window=window, scale=scale,
+                                                softclamp=softclamp, q_pos_offset=q_off, dq_acc=dq_acc,
+                                                dkv_acc_ptrs=acc_ptrs, nk_pad=nk_pad, ready=ready,
+                                                ready_target=ready_target, hop_owner=hop_owner)
+                dq = torch.empty(b, n_q, h, d_pad, dtype=dt, device=dev)
+                ops.acc_convert(dq_acc, dq, scale)
+                _count(2)
+            if use_ring:
+                with nvtx_range("rab.bwd.barrier+convert"):
+                    torch.cuda.current_stream(dev).wait_event(side_done)
+                    ws.barrier()  # every rank's kernel has finished adding into this rank's accumulators
+                    dk = torch.empty(b, n_k, hk, d_pad, dtype=dt, device=dev)
+                    dv = torch.empty_like(dk)
+                    ops.acc_convert(acc[0], dk, 1.0)
+                    ops.acc_convert(acc[1], dv, 1.0)
+                    _count(3)
+        else:
+            # ---------------- two-kernel backward (csrc/attn_bwd_sm100.cu) ----------------
+            qdo_gather = alloc_qdo_buffer(ring_size, b, h, n_q, d_pad, dt, dev)
+            stat_gather = alloc_stat_buffer(ring_size, b, h, n_q, dev)
+            ops.bwd_prep(qp, o, dop, lse, qdo_gather, stat_gather, rank)
+            _count()
+            ready_kv, gather_done = None, None
+            if use_ring:
+                qdo_bytes = qdo_gather[rank].numel() * qdo_gather.element_size()
+                stat_bytes = stat_gather[rank].numel() * 4
+                stage, peer_ptrs = ws.staging("qdo", qdo_bytes + stat_bytes)
+                stage[:qdo_bytes].copy_(qdo_gather[rank].view(torch.uint8).reshape(-1))
+                stage[qdo_bytes:qdo_bytes + stat_bytes].copy_(stat_gather[rank].view(torch.uint8).reshape(-1))
+                ws.barrier()
+                _count(3)
+                ready_kv, _ = pull_kv_slots()  # K/V first: the dQ kernel consumes it hop by hop
+                q_owners = ring_query_owners(pm, rank, causal, window)
+                with torch.cuda.stream(ws.side_stream):
+                    for o_rank in q_owners[1:]:
+                        ops.peer_copy(qdo_gather[o_rank], peer_ptrs[o_rank], qdo_bytes)
+                        ops.peer_copy(stat_gather[o_rank], peer_ptrs[o_rank] + qdo_bytes, stat_bytes)
+                    gather_done = torch.cuda.Event()
+                    gather_done.record(ws.side_stream)
+                qdo_gather.record_stream(ws.side_stream)
+                stat_gather.record_stream(ws.side_stream)
+            common = (kbits, b, h, hk, rank, bool(causal), int(window or 0), float(scale), float(softclamp), pm.stride,
+                      pm.seg_len, pm.base0, pm.base1, int(q_off))
+            # dQ only needs the K/V slots (flag per owner): it overlaps with the Q/dO gather
+            dq = ops.attn_bwd_dq(qdo_gather, kv_gather, stat_gather, ready_kv, 1 if ready_kv is not None else 0, *common,
+                                 hop_owner)
+            if gather_done is not None:
+                torch.cuda.current_stream(dev).wait_event(gather_done)
+            dk, dv = ops.attn_bwd_dkdv(qdo_gather, kv_gather, stat_gather, None, 0, *common,
+                                       ring_query_owners(pm, rank, causal, window))
+            _count(2)
 
         dq, dk, dv = dq[..., :d], dk[..., :d], dv[..., :d]
         if orig_dtype != dt:

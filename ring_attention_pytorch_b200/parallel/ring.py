@@ -1,19 +1,23 @@
-"""Ring topology arithmetic and the host-driven P2P ring used by the pure-PyTorch (CPU / gloo) path.
+"""Host-driven P2P ring for the portable (CPU / gloo, or NCCL without the sm_100a kernels) path.
 
-The sm_100a path does not use this module on its hot path – there the "ring" is a schedule evaluated
-inside the kernel and K/V move with in-kernel bulk-TMA copies over NVLink (csrc/attn_fwd_sm100.cu).
-This module keeps the reference's functional surface (reference ring.py:27-124) for the portable path
-and for users that built on it, with these differences:
+The sm_100a path never touches this module: there the ring is a *schedule* evaluated inside the kernels
+(``layout.ring_hop_owners`` -> ``hop_owner[]``) and K/V move with in-kernel bulk-TMA copies over NVLink.  The
+portable path follows the same schedule — hop ``s`` of ring rank ``r`` holds the data of owner ``(r - s) mod W`` —
+and realises it by actually rotating the tensors with point-to-point messages, so both backends share one definition
+of "who is visited when" (:class:`RingTopology`).
 
-* no ``dist.barrier()`` after every exchange (reference ring.py:57-60) – ``batch_isend_irecv`` + wait is
-  already a complete point-to-point synchronisation;
-* ``ring_pass`` honours ``num_ring_passes`` (reference ring.py:62-77 ignores it);
-* ring sets (``ring_size < world_size``) always use ring-local arithmetic.
+The reference's functional surface (reference ring.py:27-124: ``circular_*``, ``ring_pass``, ``one_ring_pass``,
+``null_ring_pass``, ``all_ring_pass``, ``RingInfo``) is kept for users that built on it.  Differences in behaviour:
+
+* no ``dist.barrier()`` after every exchange (reference ring.py:57-60): a matched isend / irecv pair that has been
+  waited on is already a complete point-to-point synchronisation;
+* ``ring_pass`` honours ``num_ring_passes`` (reference ring.py:62-77 always moves one position);
+* ranks and owners handed to callers are ring-local, also for ring sets (``ring_size < world_size``).
 """
 from __future__ import annotations
 
-from collections import namedtuple
-from typing import Optional
+from dataclasses import dataclass
+from typing import Iterator, List, NamedTuple, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -22,8 +26,34 @@ from torch import Tensor
 from ring_attention_pytorch_b200.parallel.distributed import default, exists, get_rank, get_world_size
 
 
+@dataclass(frozen=True)
+class RingTopology:
+    """One ring set: global ranks ``[base, base + size)``; ``local`` is this rank's position inside it."""
+    size: int
+    base: int
+    local: int
+
+    @classmethod
+    def of(cls, rank: Optional[int] = None, ring_size: Optional[int] = None) -> "RingTopology":
+        rank = default(rank, get_rank())
+        size = max(1, default(ring_size, get_world_size()))
+        return cls(size=size, base=(rank // size) * size, local=rank % size)
+
+    def shifted(self, steps: int) -> int:
+        """Ring-local index ``steps`` positions to the right (negative: left)."""
+        return (self.local + steps) % self.size
+
+    def to_global(self, local_index: int) -> int:
+        return self.base + local_index % self.size
+
+    def owner_at_hop(self, hop: int) -> int:
+        """Ring-local rank whose shard this rank holds after ``hop`` exchanges (same rule as the kernels' schedule)."""
+        return self.shifted(-hop)
+
+
+# ---- reference-compatible index helpers (reference ring.py:27-47) -----------------------------------------------------
 def circular_index_left(pos: int, ring_size: int, num: int = 1) -> int:
-    return ((pos - num) + ring_size) % ring_size
+    return (pos - num) % ring_size
 
 
 def circular_index_right(pos: int, ring_size: int, num: int = 1) -> int:
@@ -31,47 +61,40 @@ def circular_index_right(pos: int, ring_size: int, num: int = 1) -> int:
 
 
 def circular_rank_left(rank: Optional[int] = None, ring_size: Optional[int] = None, num: int = 1) -> int:
-    rank = default(rank, get_rank())
-    ring_size = default(ring_size, get_world_size())
-    ring_set_num = rank // ring_size
-    offset = ring_set_num * ring_size
-    return circular_index_left(rank, ring_size, num) + offset
+    topo = RingTopology.of(rank, ring_size)
+    return topo.to_global(topo.shifted(-num))
 
 
 def circular_rank_right(rank: Optional[int] = None, ring_size: Optional[int] = None, num: int = 1) -> int:
-    rank = default(rank, get_rank())
-    ring_size = default(ring_size, get_world_size())
-    ring_set_num = rank // ring_size
-    offset = ring_set_num * ring_size
-    return circular_index_right(rank, ring_size, num) + offset
+    topo = RingTopology.of(rank, ring_size)
+    return topo.to_global(topo.shifted(num))
 
 
+# ---- data movement ---------------------------------------------------------------------------------------------------
 def send_and_receive_(x: Tensor, receive_buffer: Tensor, send_to_rank: int, receive_from_rank: int) -> None:
-    """One ring exchange (reference ring.py:51-60, minus the global barrier)."""
-    ops = [dist.P2POp(dist.isend, x, send_to_rank), dist.P2POp(dist.irecv, receive_buffer, receive_from_rank)]
-    for req in dist.batch_isend_irecv(ops):
-        req.wait()
+    """One matched exchange; returns when both directions have completed."""
+    work = dist.batch_isend_irecv([
+        dist.P2POp(dist.isend, x, send_to_rank),
+        dist.P2POp(dist.irecv, receive_buffer, receive_from_rank),
+    ])
+    for w in work:
+        w.wait()
 
 
 def ring_pass(num_ring_passes: int, x: Tensor, receive_buffer: Optional[Tensor] = None, ring_size: Optional[int] = None):
     """Move ``x`` ``num_ring_passes`` positions to the right around this rank's ring set.
 
-    Returns ``(received, sent)`` like the reference so the sent tensor can be reused as the next receive
-    buffer (reference ring.py:62-77).
+    Returns ``(received, sent)``: the sent tensor can serve as the next receive buffer, which is how the portable ring
+    op ping-pongs two allocations through all hops.
     """
-    ring_size = default(ring_size, get_world_size())
+    topo = RingTopology.of(ring_size=ring_size)
     x = x.contiguous()
-    if not exists(receive_buffer):
-        receive_buffer = torch.zeros_like(x)
-    else:
-        receive_buffer = receive_buffer.contiguous()
-    num = num_ring_passes % ring_size if ring_size > 0 else 0
-    if num == 0:
+    receive_buffer = torch.empty_like(x) if not exists(receive_buffer) else receive_buffer.contiguous()
+    steps = num_ring_passes % topo.size
+    if steps == 0:
         receive_buffer.copy_(x)
         return receive_buffer, x
-    left = circular_rank_left(ring_size=ring_size, num=num)
-    right = circular_rank_right(ring_size=ring_size, num=num)
-    send_and_receive_(x, receive_buffer, right, left)
+    send_and_receive_(x, receive_buffer, topo.to_global(topo.shifted(steps)), topo.to_global(topo.shifted(-steps)))
     return receive_buffer, x
 
 
@@ -79,36 +102,31 @@ def one_ring_pass(x: Tensor, receive_buffer: Optional[Tensor] = None, ring_size:
     return ring_pass(1, x, receive_buffer, ring_size)
 
 
-RingInfo = namedtuple("RingInfo", ["ring_rank", "iter_info"])
+class RingInfo(NamedTuple):
+    ring_rank: int                 # ring-local rank of the shard currently held
+    iter_info: Tuple[bool, bool]   # (first hop, last hop)
 
 
 def null_ring_pass(*tensors, max_iters=None, receive_buffers=None, ring_size=None):
-    """reference ring.py:85-86"""
+    """Degenerate ring of one hop (no communication): what the ring iterator yields without sequence parallelism."""
     yield RingInfo(0, (True, True)), (tensors, receive_buffers)
 
 
-def all_ring_pass(*tensors, max_iters: Optional[int] = None, receive_buffers=None, ring_size: Optional[int] = None):
-    """Iterate over the ring: yields the tensors currently held together with the ring-local rank of the
-    rank that produced them (reference ring.py:88-124; here ``ring_rank`` is always ring-local)."""
-    ring_size = default(ring_size, get_world_size())
-    max_iters = default(max_iters, ring_size)
-    receive_buffers = default(receive_buffers, (None,) * len(tensors))
-    total_iters = max(1, min(ring_size, max_iters))
+def all_ring_pass(*tensors, max_iters: Optional[int] = None, receive_buffers: Optional[Sequence] = None,
+                  ring_size: Optional[int] = None) -> Iterator:
+    """Visit the ring: yields, hop by hop, the tensors currently held and the ring-local rank that owns them.
 
-    curr_ring_pos = get_rank() % ring_size
-    for ind in range(total_iters):
-        is_first, is_last = ind == 0, ind == total_iters - 1
-        yield RingInfo(curr_ring_pos, (is_first, is_last)), (tensors, receive_buffers)
-        curr_ring_pos = circular_index_left(curr_ring_pos, ring_size)
-        if is_last:
-            continue
-        new_tensors, new_buffers = [], []
-        for tensor, buffer in zip(tensors, receive_buffers):
-            if not exists(tensor):
-                new_tensors.append(None)
-                new_buffers.append(None)
-                continue
-            new_tensor, new_buffer = one_ring_pass(tensor, buffer, ring_size)
-            new_tensors.append(new_tensor)
-            new_buffers.append(new_buffer)
-        tensors, receive_buffers = new_tensors, new_buffers
+    ``max_iters`` truncates the walk (causal look-back limits); ``None`` entries in ``tensors`` travel as ``None``.
+    """
+    topo = RingTopology.of(ring_size=ring_size)
+    hops = max(1, min(topo.size, default(max_iters, topo.size)))
+    held: List[Optional[Tensor]] = list(tensors)
+    spare: List[Optional[Tensor]] = list(default(receive_buffers, (None,) * len(tensors)))
+    for hop in range(hops):
+        last = hop == hops - 1
+        yield RingInfo(topo.owner_at_hop(hop), (hop == 0, last)), (held, spare)
+        if last:
+            break
+        moved = [ring_pass(1, t, buf, topo.size) if exists(t) else (None, None) for t, buf in zip(held, spare)]
+        held = [m[0] for m in moved]
+        spare = [m[1] for m in moved]

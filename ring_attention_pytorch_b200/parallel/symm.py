@@ -70,11 +70,40 @@ class RingWorkspace:
         return region
 
     def region(self, name: str, nbytes: int) -> SymmRegion:
-        """Return a symmetric region of at least ``nbytes`` (collective on first use / growth)."""
+        """Return a symmetric region of at least ``nbytes`` (collective on first use / growth).
+
+        Growth retires the old region first.  Peers may still be reading it over NVLink (fused kernels, copy-engine
+        pulls of the previous call), and freeing IPC-exported memory under an importer is undefined, so the retirement
+        is a collective fence: every rank drains its own device work, all ranks meet, imports are closed, and only then
+        is the exporting allocation released."""
         reg = self.regions.get(name)
-        if reg is None or reg.nbytes < nbytes:
-            reg = self._alloc(name, nbytes)
-        return reg
+        if reg is not None and reg.nbytes >= nbytes:
+            return reg
+        if reg is not None:
+            self._retire(name)
+        return self._alloc(name, nbytes)
+
+    def _retire(self, name: str) -> None:
+        reg = self.regions.pop(name)
+        self.uses.pop(name, None)
+        torch.cuda.synchronize(self.device)
+        if self.ring_size > 1:
+            dist.barrier(group=self.group)  # every rank has finished all work that could touch the old region
+        ops = _ext.ops()
+        for r, ptr in enumerate(reg.peer_ptrs):
+            if r != self.ring_rank:
+                ops.symm_close(ptr)
+        if self.ring_size > 1:
+            dist.barrier(group=self.group)  # all imports are closed: the exporters may free
+        del reg  # drops the local tensor -> cudaFree through the from_blob deleter
+
+    def close(self) -> None:
+        """Release every region (collective).  Called at interpreter exit for the cached workspaces."""
+        for name in list(self.regions):
+            if name != "__pads__":
+                self._retire(name)
+        if "__pads__" in self.regions:
+            self._retire("__pads__")
 
     def staging(self, name: str, nbytes: int) -> Tuple[torch.Tensor, List[int]]:
         """Double-buffered staging slot: returns (local uint8 view, peer base pointers of the same half).
@@ -101,6 +130,16 @@ class RingWorkspace:
 
 
 _workspaces: Dict[Tuple[int, int, int], RingWorkspace] = {}
+
+
+def close_workspaces() -> None:
+    """Collective: retire every cached workspace (tests call it before tearing the process group down)."""
+    for key in list(_workspaces):
+        ws = _workspaces.pop(key)
+        try:
+            ws.close()
+        except Exception:  # noqa: BLE001 - best effort at shutdown (the process group may already be gone)
+            pass
 
 
 def get_workspace(ring_size: int, device: torch.device) -> RingWorkspace:

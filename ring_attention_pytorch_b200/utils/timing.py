@@ -2,7 +2,7 @@
 from __future__ import annotations
 
 import contextlib
-from typing import Callable, List
+from typing import Callable, Dict, List
 
 import torch
 import torch.distributed as dist
@@ -36,13 +36,48 @@ def max_over_ranks(ms: float) -> float:
     return float(t.item())
 
 
+# Phase timeline: every ``nvtx_range`` of the ring op (pack+barrier / kernel / prep / zero+barrier / convert ...) also
+# records a pair of CUDA events while ``enable_phase_timing(True)`` is in effect; ``phase_report()`` turns them into
+# per-phase milliseconds of this rank (tools/phase_timeline.py prints the table for every rank of a ring).
+_PHASES = None
+
+
+def enable_phase_timing(on: bool = True) -> None:
+    global _PHASES
+    _PHASES = [] if on else None
+
+
+def phase_report(reset: bool = True) -> Dict[str, List[float]]:
+    """{phase name: [ms of every occurrence]} since phase timing was enabled (synchronises the device)."""
+    global _PHASES
+    out: Dict[str, List[float]] = {}
+    if _PHASES is None:
+        return out
+    torch.cuda.synchronize()
+    for name, e0, e1 in _PHASES:
+        out.setdefault(name, []).append(e0.elapsed_time(e1))
+    if reset:
+        _PHASES = []
+    return out
+
+
 @contextlib.contextmanager
 def nvtx_range(name: str):
-    torch.cuda.nvtx.range_push(name)
+    on_gpu = torch.cuda.is_available()
+    if on_gpu:
+        torch.cuda.nvtx.range_push(name)
+    ev = None
+    if _PHASES is not None and on_gpu:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     try:
         yield
     finally:
-        torch.cuda.nvtx.range_pop()
+        if ev is not None:
+            ev[1].record()
+            _PHASES.append((name, ev[0], ev[1]))
+        if on_gpu:
+            torch.cuda.nvtx.range_pop()
 
 
 def attention_flops(batch: int, heads: int, seq_q: int, seq_k: int, dim: int, causal: bool, backward: bool = False):

@@ -57,9 +57,8 @@ def case_probe(mode: int, variant: str = "base"):
 
 
 def case_probe_mn_a(k: int = 128):
-    """Not validated yet (written after the last GPU minute of round 1): MN-major A from shared memory plus a B tile
-    written by the threads with a hand-applied 128B swizzle — the two operand flavours a one-kernel (5-GEMM) backward
-    needs for dQ^T = K^T dS^T.  Run with ``--only xprobe_mn_a``."""
+    """MN-major A from shared memory plus a B tile written by the threads with a hand-applied 128B swizzle — the two
+    operand flavours the one-kernel (5-GEMM) backward needs for dQ^T = K^T dS^T."""
     import torch
     from ring_attention_pytorch_b200.ops import _ext
 
@@ -74,34 +73,6 @@ def case_probe_mn_a(k: int = 128):
     err = (out - ref).abs().max().item()
     rel = err / ref.abs().max().item()
     return {"max_abs_err": err, "rel": rel, "ok": rel < 2e-2}
-
-
-def case_fused_bwd(causal=True, n=1024, h=4, hk=4, b=2):
-    """Not validated yet: the experimental one-kernel backward (CONFIG['fused_backward']) against the two-kernel one and
-    the fp32 oracle, plus timings of both."""
-    import torch
-    from ring_attention_pytorch_b200.ops import ring_cuda
-    from ring_attention_pytorch_b200.ops.oracle import default_attention
-
-    torch.manual_seed(0)
-    q, k, v = (torch.randn(b, n, hh, 128, device="cuda", dtype=torch.bfloat16, requires_grad=True) for hh in (h, hk, hk))
-    g = torch.randn(b, n, h, 128, device="cuda", dtype=torch.bfloat16)
-    res = {}
-    grads = {}
-    for name, flag in (("two_kernel", False), ("one_kernel", True)):
-        ring_cuda.CONFIG["fused_backward"] = flag
-        out = ring_cuda.ring_flash_attn_cuda(q, k, v, None, causal)
-        grads[name] = torch.autograd.grad(out, (q, k, v), g)
-    ring_cuda.CONFIG["fused_backward"] = False
-    qf, kf, vf = (t.detach().float().requires_grad_() for t in (q, k, v))
-    want = torch.autograd.grad(default_attention(qf, kf, vf, causal=causal), (qf, kf, vf), g.float())
-    ok = True
-    for name in grads:
-        rel = [((a.float() - w).abs().max() / w.abs().max()).item() for a, w in zip(grads[name], want)]
-        res[name] = rel
-        ok = ok and all(r < 3e-2 for r in rel)
-    res["ok"] = ok
-    return res
 
 
 def _ref_ring(qs, ks, vs, layout, causal, window, softclamp, key_masks):
@@ -152,7 +123,7 @@ def case_fwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=Fa
 
 
 def case_bwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=False, window=None, softclamp=0.0,
-             kmask=False, dtype="bf16", seed=0):
+             kmask=False, dtype="bf16", seed=0, fused=None):
     import torch
     from ring_attention_pytorch_b200.ops.fused import emulate_ring_backward, emulate_ring_forward
     from ring_attention_pytorch_b200.ops.oracle import attention_with_positions
@@ -171,7 +142,7 @@ def case_bwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=Fa
     outs, lses = emulate_ring_forward(qs, ks, vs, layout=layout, causal=causal, window=window, softclamp=softclamp,
                                       key_masks=kms)
     grads = emulate_ring_backward(qs, ks, vs, outs, lses, dos, layout=layout, causal=causal, window=window,
-                                  softclamp=softclamp, key_masks=kms)
+                                  softclamp=softclamp, key_masks=kms, fused=fused)
     torch.cuda.synchronize()
     # fp32 oracle through autograd
     pm = make_position_map(layout, world, n)
@@ -213,6 +184,72 @@ def case_bwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=Fa
                 detail[f"r{r}_{name}"] = [[round(x, 3) for x in row] for row in tile[0].tolist()]
         res["detail_b0_tile_by_head"] = detail
     return res
+
+
+def case_perf_bwd_fused(n=16384, h=16, causal=True, iters=5, b=1, hk=None):
+    """The one-kernel backward (prep + kernel + dQ convert), timed like case_perf_bwd."""
+    import torch
+    from ring_attention_pytorch_b200.ops import _ext
+    from ring_attention_pytorch_b200.ops.fused import (alloc_kv_buffer, alloc_qdo_buffer, alloc_stat_buffer,
+                                                       fused_attn_bwd_ring, fused_attn_fwd)
+    from ring_attention_pytorch_b200.parallel.layout import make_position_map
+
+    ops = _ext.ops()
+    hk = hk or h
+    d = 128
+    dt = torch.bfloat16
+    q = torch.randn(b, n, h, d, device="cuda", dtype=dt)
+    k = torch.randn(b, n, hk, d, device="cuda", dtype=dt)
+    v = torch.randn(b, n, hk, d, device="cuda", dtype=dt)
+    do = torch.randn(b, n, h, d, device="cuda", dtype=dt)
+    pm = make_position_map("plain", 1, n)
+    kv = alloc_kv_buffer(1, b, hk, n, d, dt, "cuda")
+    qdo = alloc_qdo_buffer(1, b, h, n, d, dt, "cuda")
+    stat = alloc_stat_buffer(1, b, h, n, "cuda")
+    ops.pack_kv(k, v, kv[0])
+    ready = torch.zeros(1, dtype=torch.int32, device="cuda")
+    o, lse = fused_attn_fwd(q, kv, [0], ready, None, kv_heads=hk, rank=0, pm=pm, causal=causal, window=None,
+                            scale=d ** -0.5)
+    dq = torch.empty_like(q)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+    def run(timed=False):
+        if timed:
+            ev[0].record()
+        ops.bwd_prep(q, o, do, lse, qdo, stat, 0)
+        if timed:
+            ev[1].record()
+        acc = torch.zeros(b * h, stat.shape[-1], d, dtype=torch.float32, device="cuda")
+        if timed:
+            ev[2].record()
+        _, dk, dv = fused_attn_bwd_ring(qdo[0], stat[0], kv, None, batch=b, heads=h, kv_heads=hk, rank=0, pm=pm,
+                                        causal=causal, window=None, scale=d ** -0.5, dq_acc=acc)
+        if timed:
+            ev[3].record()
+        ops.acc_convert(acc, dq, d ** -0.5)
+        if timed:
+            ev[4].record()
+        return dq, dk, dv
+
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[len(times) // 2]
+    flops = 2.5 * 4.0 * b * h * n * n * d * (0.5 if causal else 1.0)
+    run(timed=True)
+    torch.cuda.synchronize()
+    return {"ms": ms, "tflops_5gemm": flops / ms / 1e9, "ms_prep": ev[0].elapsed_time(ev[1]),
+            "ms_zero": ev[1].elapsed_time(ev[2]), "ms_kernel": ev[2].elapsed_time(ev[3]),
+            "ms_convert": ev[3].elapsed_time(ev[4]), "tflops_kernel_only": flops / ev[2].elapsed_time(ev[3]) / 1e9,
+            "ok": True}
 
 
 def case_perf_bwd(n=16384, h=16, d=128, causal=True, iters=5, b=1, hk=None):
@@ -408,10 +445,8 @@ CASES = {
     "ring3_kmask": lambda: case_fwd(world=3, n=200, h=2, kmask=True),
     "ring8_striped_causal_big": lambda: case_fwd(world=8, n=1024, h=8, hk=2, layout="striped", causal=True),
     # backward, single rank
-    "xfused_bwd_causal": lambda: case_fused_bwd(causal=True),
-    "xfused_bwd_full_gqa": lambda: case_fused_bwd(causal=False, hk=2, n=700),
-    "xprobe_mn_a": lambda: case_probe_mn_a(),
-    "xprobe_mn_a_k64": lambda: case_probe_mn_a(64),
+    "probe_mn_a": lambda: case_probe_mn_a(),
+    "probe_mn_a_k64": lambda: case_probe_mn_a(64),
     "bwd_d128_n256": lambda: case_bwd(),
     "bwd_d128_n128_h1": lambda: case_bwd(n=128, h=1),
     "bwd_d128_n64_h1": lambda: case_bwd(n=64, h=1),
@@ -437,7 +472,15 @@ CASES = {
     "rbwd4_zigzag_causal": lambda: case_bwd(world=4, n=512, h=2, layout="zigzag", causal=True),
     "rbwd4_plain_window": lambda: case_bwd(world=4, n=256, h=2, causal=True, window=300),
     "rbwd3_kmask": lambda: case_bwd(world=3, n=200, h=2, kmask=True),
+    # the two-kernel backward at head dim 128 (the default there is the one-kernel backward)
+    "bwd2k_d128_causal_n1000": lambda: case_bwd(n=1000, causal=True, h=4, fused=False),
+    "bwd2k_gqa_causal": lambda: case_bwd(n=512, h=8, hk=2, causal=True, fused=False),
+    "bwd2k_ring4_striped_causal": lambda: case_bwd(world=4, n=384, h=4, hk=2, layout="striped", causal=True, fused=False),
     # performance
+    "perffz_causal_16k": lambda: case_perf_bwd_fused(),
+    "perffz_full_8k": lambda: case_perf_bwd_fused(n=8192, causal=False),
+    "perffz_causal_64k_h8": lambda: case_perf_bwd_fused(n=65536, h=8, iters=3),
+    "perffz_gqa_causal_32k": lambda: case_perf_bwd_fused(n=32768, h=16, hk=4, iters=3),
     "perfbwd_causal_16k": lambda: case_perf_bwd(),
     "perfbwd_full_8k": lambda: case_perf_bwd(n=8192, causal=False),
     "perfbwd_causal_64k_h8": lambda: case_perf_bwd(n=65536, h=8, iters=3),
@@ -456,6 +499,8 @@ GROUPS = {
     "ring": [c for c in CASES if c.startswith("ring")],
     "bwd": [c for c in CASES if c.startswith("bwd")],
     "rbwd": [c for c in CASES if c.startswith("rbwd")],
+    "bwd2k": [c for c in CASES if c.startswith("bwd2k")],
+    "perffz": [c for c in CASES if c.startswith("perffz")],
     "perfbwd": [c for c in CASES if c.startswith("perfbwd")],
     "perfdec": [c for c in CASES if c.startswith("perfdec")],
     "perf": [c for c in CASES if c.startswith("perf_")],
@@ -468,6 +513,7 @@ def main():
     ap.add_argument("--only", default="probe,fwd,ring,perf")
     ap.add_argument("--timeout", type=int, default=150)
     ap.add_argument("--log", default=os.path.join(ROOT, "gpurun_out", "dev_check.log"))
+    ap.add_argument("--max-fail", type=int, default=0, help="stop after this many failed cases (0: never)")
     args = ap.parse_args()
 
     if args.case:
@@ -480,6 +526,7 @@ def main():
     for g in args.only.split(","):
         names += GROUPS.get(g, [g] if g in CASES else [])
     summary = []
+    nfail = 0
     with open(args.log, "a") as log:
         log.write(f"\n==== dev check {time.strftime('%F %T')} only={args.only}\n")
         for name in names:
@@ -501,7 +548,11 @@ def main():
             log.write(msg + "\n")
             if not status.startswith("{") or '"ok": false' in status:
                 log.write("---- output tail\n" + out[-3000:] + "\n----\n")
+                nfail += 1
             log.flush()
+            if args.max_fail and nfail >= args.max_fail:
+                print(f"stopping after {nfail} failed cases", flush=True)
+                break
 
 
 if __name__ == "__main__":
