@@ -24,11 +24,12 @@
 // Warp roles (384 threads, 1 CTA / SM, persistent):
 //   warps 0-3 / 4-7 : warpgroup of stream 0 / 1 (even / odd steps): softmax algebra, dS^T to smem, dQ^T drain, epilogue
 //   warp 8          : TMA producer (K/V tile per item; Q, dO, lse, delta per step; 3-stage ring)
-//   warp 9          : S issuer    : S^T(j) into X_w
-//   warp 10         : acc issuer  : dP^T(j) into Y_w, then dV, dK and dQ^T(j) (dQ^T reuses X_w once S^T is in registers)
-// TMEM (512 columns): stream w: X_w = [128 w, +64): S^T -> P^T (16 bit, 32 columns) -> dQ^T;  Y_w = [128 w + 64, +64):
-// dP^T -> dS^T (16 bit); dK = [256, 384), dV = [384, 512).  All tcgen05.mma that touch X_w after S^T (dV reading P^T,
-// dQ^T overwriting it) are issued by ONE thread in that order, so the tensor pipe's in-order execution keeps them apart.
+//   warp 9          : logit issuer: S^T(j) into X_w (two steps ahead) and dP^T(j) into Y_w
+//   warp 10         : acc issuer  : dV, dK and dQ^T(j) once the warpgroup has handed P^T | dS^T over
+// TMEM (512 columns): stream w: X_w = [128 w, +64): S^T only (refilled as soon as it has been pulled into registers);
+// Y_w = [128 w + 64, +64): dP^T -> P^T | dS^T (16 bit, 32 + 32 columns) -> dQ^T; dK = [256, 384), dV = [384, 512).
+// The tcgen05.mma that read P^T | dS^T from Y_w and the one that overwrites it with dQ^T are issued by ONE thread in that
+// order (the tensor pipe executes in order); every other reuse of a block is ordered by an mbarrier.
 #include "attn_common.cuh"
 
 namespace rab {
@@ -53,7 +54,7 @@ struct FzSmem {
   alignas(16) float delta[QST][64];
   uint64_t kv_full, kv_empty;
   uint64_t qd_full[QST], qd_empty[QST];
-  uint64_t s_full[2], dp_full[2], pds_ready[2], dq_full[2], x_free[2];
+  uint64_t s_full[2], s_free[2], dp_full[2], pds_ready[2], dq_full[2], y_free[2];
   uint64_t acc_done, epi_done;
   uint32_t tmem_base;
 };
@@ -172,17 +173,22 @@ __device__ __forceinline__ void fz_producer(FzSmem& sm, const AttnBwdFusedParams
 }
 
 // ------------------------------------------------------------------------------------------------
-// warp 9: S issuer.  S^T(j) = K Q^T into X_w; X_w is free once dQ^T of this stream's previous step has been drained.
+// warp 9: logit issuer.  Per step j (stream w = j & 1):
+//    S^T(j)  = K Q^T  into X_w   as soon as the warpgroup has pulled S^T(j-2) into registers        (s_free[w])
+//    dP^T(j) = V dO^T into Y_w   as soon as the warpgroup has drained dQ^T(j-2) out of the block    (y_free[w])
+// Issue order S(0) S(1) | dP(0) S(2) | dP(1) S(3) | ... follows the order in which those events happen, so every
+// wait is a blocking in-order mbarrier wait and S^T runs two steps ahead of the warpgroup.
 // ------------------------------------------------------------------------------------------------
 template <bool BF16>
-__device__ __forceinline__ void fz_issue_s(FzSmem& sm, const AttnBwdFusedParams& p, uint32_t tmem_in) {
+__device__ __forceinline__ void fz_issue_logits(FzSmem& sm, const AttnBwdFusedParams& p, uint32_t tmem_in) {
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);
   constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
   constexpr uint32_t STAGE16 = FzSmem::Q_TILE >> 4;
   const int lane = lane_id();
   const uint32_t tmem = warp_uniform(tmem_in);
   uint32_t n_item = 0, tile_base = 0;
-  uint32_t c_s[2] = {0, 0};  // S^T issued per stream (cumulative): x_free parity
+  uint32_t c_s[2] = {0, 0};  // S^T issued per stream (cumulative): s_free parity
+  uint32_t c_p[2] = {0, 0};  // dP^T issued per stream (cumulative): y_free parity
   const int total = fz_num_items(p);
   for (int L = blockIdx.x; L < total; L += gridDim.x, ++n_item) {
     FzItem it;
@@ -192,14 +198,16 @@ __device__ __forceinline__ void fz_issue_s(FzSmem& sm, const AttnBwdFusedParams&
     const uint32_t ntiles = scan.count(lane);
     mbar_wait(&sm.kv_full, n_item & 1, 1200);
     tc_fence_after();
-    const uint64_t k_desc = umma_desc(kmaj, smem_u32(sm.k));
+    const uint64_t k_desc = umma_desc(kmaj, smem_u32(sm.k)), v_desc = umma_desc(kmaj, smem_u32(sm.v));
     const uint64_t q_kdesc0 = umma_desc(kmaj, smem_u32(sm.q[0]));
-    for (uint32_t j = 0; j < ntiles; ++j) {
+    const uint64_t do_kdesc0 = umma_desc(kmaj, smem_u32(sm.dout[0]));
+
+    auto issue_s = [&](uint32_t j) {
       const uint32_t w = j & 1u;
       const uint32_t g = tile_base + j;
       const uint32_t st = g % QST, ph = (g / QST) & 1;
       mbar_wait(&sm.qd_full[st], ph, 1210 + st);
-      if (c_s[w] > 0) mbar_wait(&sm.x_free[w], (c_s[w] - 1u) & 1, 1220 + w);
+      if (c_s[w] > 0) mbar_wait(&sm.s_free[w], (c_s[w] - 1u) & 1, 1220 + w);
       tc_fence_after();
       const uint32_t x_tm = tmem + w * 128u;
       const uint64_t qk = q_kdesc0 + uint64_t(st * STAGE16);
@@ -214,50 +222,13 @@ __device__ __forceinline__ void fz_issue_s(FzSmem& sm, const AttnBwdFusedParams&
       }
       __syncwarp();
       c_s[w]++;
-    }
-    umma_commit_w(&sm.kv_empty);  // second arrival comes from the acc issuer
-    tile_base += ntiles;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// warp 10: acc issuer.  dP^T(j) into Y_w (two steps ahead), then dV += P^T dO, dK += dS^T Q, dQ^T(j) = K^T dS^T into X_w.
-// ------------------------------------------------------------------------------------------------
-template <bool BF16>
-__device__ __forceinline__ void fz_issue_acc(FzSmem& sm, const AttnBwdFusedParams& p, uint32_t tmem_in) {
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0, BF16 ? 1 : 0);
-  constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);
-  constexpr uint32_t idesc_dqt = umma_idesc_bf16(D, 64, 1, 1, BF16 ? 1 : 0);
-  constexpr uint64_t kmaj = umma_smem_desc_hi_lo(16, 1024, UMMA_LAYOUT_SW128);
-  constexpr uint64_t mnmaj64 = umma_smem_desc_hi_lo(SUB64, 1024, UMMA_LAYOUT_SW128);
-  constexpr uint64_t mnmaj128 = umma_smem_desc_hi_lo(SUB128, 1024, UMMA_LAYOUT_SW128);
-  constexpr uint32_t STAGE16 = FzSmem::Q_TILE >> 4;
-  const int lane = lane_id();
-  const uint32_t tmem = warp_uniform(tmem_in);
-  const uint32_t dk_tm = tmem + 256, dv_tm = tmem + 256 + D;
-  uint32_t n_item = 0, tile_base = 0;
-  uint32_t c_b[2] = {0, 0};  // dV/dK issued per stream (cumulative): pds_ready parity
-  const int total = fz_num_items(p);
-  for (int L = blockIdx.x; L < total; L += gridDim.x, ++n_item) {
-    FzItem it;
-    fz_decode(p, L, it);
-    FzScan scan;
-    fz_init_scan(scan, p, it);
-    const uint32_t ntiles = scan.count(lane);
-    mbar_wait(&sm.kv_full, n_item & 1, 1300);
-    tc_fence_after();
-    const uint64_t v_desc = umma_desc(kmaj, smem_u32(sm.v));
-    const uint64_t k_mn = umma_desc(mnmaj128, smem_u32(sm.k));
-    const uint64_t do_kdesc0 = umma_desc(kmaj, smem_u32(sm.dout[0]));
-    const uint64_t q_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.q[0]));
-    const uint64_t do_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.dout[0]));
-    const uint64_t ds_mn0 = umma_desc(mnmaj128, smem_u32(sm.ds[0]));
-
-    auto issue_dp = [&](uint32_t j) {  // dP^T(j) = V dO^T into Y_w (free: dV/dK(j-2) precede it in this warp's FIFO)
+    };
+    auto issue_dp = [&](uint32_t j) {
       const uint32_t w = j & 1u;
       const uint32_t g = tile_base + j;
       const uint32_t st = g % QST, ph = (g / QST) & 1;
-      mbar_wait(&sm.qd_full[st], ph, 1310 + st);
+      mbar_wait(&sm.qd_full[st], ph, 1230 + st);
+      if (c_p[w] > 0) mbar_wait(&sm.y_free[w], (c_p[w] - 1u) & 1, 1240 + w);
       tc_fence_after();
       const uint32_t y_tm = tmem + w * 128u + 64u;
       const uint64_t dok = do_kdesc0 + uint64_t(st * STAGE16);
@@ -271,10 +242,50 @@ __device__ __forceinline__ void fz_issue_acc(FzSmem& sm, const AttnBwdFusedParam
         umma_commit(&sm.dp_full[w]);
       }
       __syncwarp();
+      c_p[w]++;
     };
 
-    if (ntiles > 0) issue_dp(0);
-    if (ntiles > 1) issue_dp(1);
+    if (ntiles > 0) issue_s(0);
+    if (ntiles > 1) issue_s(1);
+    for (uint32_t j = 0; j < ntiles; ++j) {
+      issue_dp(j);
+      if (j + 2 < ntiles) issue_s(j + 2);
+    }
+    umma_commit_w(&sm.kv_empty);  // second arrival comes from the acc issuer
+    tile_base += ntiles;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp 10: acc issuer.  Once the warpgroup has packed P^T | dS^T into Y_w and written dS^T to shared memory:
+//    dV += P^T dO, dK += dS^T Q (TS), then dQ^T(j) = K^T dS^T (SS) into the SAME block Y_w — the tensor pipe executes
+//    this thread's instructions in order, so the overwrite follows the reads.
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__device__ __forceinline__ void fz_issue_acc(FzSmem& sm, const AttnBwdFusedParams& p, uint32_t tmem_in) {
+  constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1, BF16 ? 1 : 0);
+  constexpr uint32_t idesc_dqt = umma_idesc_bf16(D, 64, 1, 1, BF16 ? 1 : 0);
+  constexpr uint64_t mnmaj64 = umma_smem_desc_hi_lo(SUB64, 1024, UMMA_LAYOUT_SW128);
+  constexpr uint64_t mnmaj128 = umma_smem_desc_hi_lo(SUB128, 1024, UMMA_LAYOUT_SW128);
+  constexpr uint32_t STAGE16 = FzSmem::Q_TILE >> 4;
+  const int lane = lane_id();
+  const uint32_t tmem = warp_uniform(tmem_in);
+  const uint32_t dk_tm = tmem + 256, dv_tm = tmem + 256 + D;
+  uint32_t n_item = 0, tile_base = 0;
+  uint32_t c_b[2] = {0, 0};  // batches issued per stream (cumulative): pds_ready parity
+  const int total = fz_num_items(p);
+  for (int L = blockIdx.x; L < total; L += gridDim.x, ++n_item) {
+    FzItem it;
+    fz_decode(p, L, it);
+    FzScan scan;
+    fz_init_scan(scan, p, it);
+    const uint32_t ntiles = scan.count(lane);
+    mbar_wait(&sm.kv_full, n_item & 1, 1300);
+    tc_fence_after();
+    const uint64_t k_mn = umma_desc(mnmaj128, smem_u32(sm.k));
+    const uint64_t q_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.q[0]));
+    const uint64_t do_mndesc0 = umma_desc(mnmaj64, smem_u32(sm.dout[0]));
+    const uint64_t ds_mn0 = umma_desc(mnmaj128, smem_u32(sm.ds[0]));
     for (uint32_t j = 0; j < ntiles; ++j) {
       const uint32_t w = j & 1u;
       const uint32_t st = (tile_base + j) % QST;
@@ -282,28 +293,26 @@ __device__ __forceinline__ void fz_issue_acc(FzSmem& sm, const AttnBwdFusedParam
       if (j == 0) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 1330);
       tc_fence_after();
       const uint32_t y_tm = tmem + w * 128u + 64u;
-      const uint32_t x_tm = tmem + w * 128u;
       const uint64_t qmn = q_mndesc0 + uint64_t(st * STAGE16), domn = do_mndesc0 + uint64_t(st * STAGE16);
       const uint64_t ds_mn = ds_mn0 + uint64_t(w * ((128 * 128) >> 4));
       const uint32_t acc0 = j > 0 ? 1u : 0u;
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 64 / 16; ++kk)
-          umma_ts(dv_tm, x_tm + kk * 8, umma_desc_add(domn, kk * 2048), idesc_acc, kk > 0 ? 1u : acc0);
+          umma_ts(dv_tm, y_tm + kk * 8, umma_desc_add(domn, kk * 2048), idesc_acc, kk > 0 ? 1u : acc0);
 #pragma unroll
         for (int kk = 0; kk < 64 / 16; ++kk)
-          umma_ts(dk_tm, y_tm + kk * 8, umma_desc_add(qmn, kk * 2048), idesc_acc, kk > 0 ? 1u : acc0);
+          umma_ts(dk_tm, y_tm + 32 + kk * 8, umma_desc_add(qmn, kk * 2048), idesc_acc, kk > 0 ? 1u : acc0);
         umma_commit(&sm.qd_empty[st]);
         // dQ^T[d, q] = K^T[d, keys] dS^T[keys, q]: A = the K tile read MN-major (like V in the forward's P V), B = the
-        // dS^T tile the warpgroup wrote to shared memory; D reuses X_w (S^T of this step is long in registers)
+        // dS^T tile the warpgroup wrote to shared memory
 #pragma unroll
         for (int kk = 0; kk < 128 / 16; ++kk)
-          umma_ss(x_tm, umma_desc_add(k_mn, kk * 2048), umma_desc_add(ds_mn, kk * 2048), idesc_dqt, kk > 0);
+          umma_ss(y_tm, umma_desc_add(k_mn, kk * 2048), umma_desc_add(ds_mn, kk * 2048), idesc_dqt, kk > 0);
         umma_commit(&sm.dq_full[w]);
       }
       __syncwarp();
       c_b[w]++;
-      if (j + 2 < ntiles) issue_dp(j + 2);
     }
     if (ntiles == 0) mbar_wait(&sm.epi_done, (n_item & 1) ^ 1, 1331);
     umma_commit_w(&sm.acc_done);
@@ -313,9 +322,15 @@ __device__ __forceinline__ void fz_issue_acc(FzSmem& sm, const AttnBwdFusedParam
 }
 
 // ------------------------------------------------------------------------------------------------
-// warps 0-7: the two warpgroups (thread = key row of the stationary tile = TMEM lane)
+// warps 0-7: the two warpgroups (thread = key row of the stationary tile = TMEM lane).  Software pipelined per stream:
+//
+//     A1(k)   : S^T(k) -> registers (frees X_w: s_free), P = exp2(S^T c - lse) with the mask applied, kept as fp32
+//     A2(k)   : dP^T(k) -> registers, dS^T = P o (dP^T - delta); P^T | dS^T packed into Y_w, dS^T to shared memory,
+//               arrive pds_ready  (warp 10 now issues dV, dK, dQ^T(k))
+//     A1(k+1) : runs while the tensor core works on the batch of step k
+//     drain(k): dQ^T(k) Y_w -> registers -> shared memory boxes -> TMA reduce-add; frees Y_w (y_free)
 // ------------------------------------------------------------------------------------------------
-template <bool BF16, bool RING>
+template <bool BF16, bool RING, bool CLAMP>
 __device__ __forceinline__ void fz_softmax(FzSmem& sm, const AttnBwdFusedParams& p, const int W, uint32_t tmem,
                                            const CUtensorMap* map_dq, const CUtensorMap* map_dkv) {
   const int wg_tid = threadIdx.x - 128 * W;
@@ -324,15 +339,14 @@ __device__ __forceinline__ void fz_softmax(FzSmem& sm, const AttnBwdFusedParams&
   const uint32_t x_tm = tmem + W * 128 + lane_off;
   const uint32_t y_tm = tmem + W * 128 + 64 + lane_off;
   const int lane = lane_id();
-  uint32_t cnt = 0, n_item = 0, tile_base = 0;
+  uint32_t n_a1 = 0, n_done = 0, n_item = 0, tile_base = 0;  // A1 passes / completed steps of this stream (cumulative)
   // per-warp drain staging: A aliases this warp's 32 rows of the dS^T tile, B is private
   uint8_t* const buf_a = sm.ds[W] + wq * 4096;
   uint8_t* const buf_b = sm.stg[W] + wq * 4096;
 
-  const bool clamp = p.softclamp > 0.f;
-  const float mul = clamp ? 1.f : p.scale * kLog2e;
-  const float pre = clamp ? p.scale / p.softclamp : 0.f;
-  const float post = clamp ? p.softclamp * kLog2e : 0.f;
+  const float mul = CLAMP ? 1.f : p.scale * kLog2e;
+  const float pre = CLAMP ? p.scale / p.softclamp : 0.f;
+  const float post = CLAMP ? p.softclamp * kLog2e : 0.f;
 
   const int total = fz_num_items(p);
   for (int L = blockIdx.x; L < total; L += gridDim.x, ++n_item) {
@@ -348,67 +362,44 @@ __device__ __forceinline__ void fz_softmax(FzSmem& sm, const AttnBwdFusedParams&
 
     FzScan scan;
     fz_init_scan(scan, p, it);
-    ScanTile t;
     uint32_t jn = 0;
-    while (scan.next(lane, t)) {
-      const uint32_t jj = jn++;
-      if ((jj & 1u) != (uint32_t)W) continue;
+    // next tile of THIS stream (tiles alternate between the two warpgroups); both walk the whole sequence
+    auto next_mine = [&](ScanTile& t, uint32_t& jj) -> bool {
+      while (scan.next(lane, t)) {
+        jj = jn++;
+        if ((jj & 1u) == (uint32_t)W) return true;
+      }
+      return false;
+    };
+
+    // ---- A1: logits -> probabilities (fp32, masked), kept in registers ------------------------------------------------
+    auto pass_a1 = [&](const ScanTile& t, const uint32_t jj, uint32_t (&sr)[64], float (&ch)[CLAMP ? 64 : 1]) {
       const uint32_t stg = (tile_base + jj) % QST;
-      uint32_t sr[64], dp[64];
-      mbar_wait(&sm.s_full[W], cnt & 1, 1400 + W);
+      mbar_wait(&sm.s_full[W], n_a1 & 1, 1400 + W);
       tc_fence_after();
       tmem_ld32(x_tm + 0, sr + 0);
       tmem_ld32(x_tm + 32, sr + 32);
       tc_wait_ld();
-
-      const int c0 = t.idx * 64;
+      tc_fence_before();
+      mbar_arrive(&sm.s_free[W]);  // X_w may take S^T of this stream's next step now
+      n_a1++;
       const float4* l4 = reinterpret_cast<const float4*>(sm.lse2[stg]);
-      const float4* d4 = reinterpret_cast<const float4*>(sm.delta[stg]);
-      uint32_t pw[32], dw[32];
-      // P^T = exp2(S^T * c - lse[col]); dS^T = P^T o (dP^T - delta[col]).  The softmax scale is folded into the dK and
-      // dQ epilogues.  The fast path has no per-element predicate; ragged / diagonal / padded tiles and the softclamp
-      // variant take the general path.
-      if (!t.part[0] && !clamp) {
+      if (!t.part[0] && !CLAMP) {
+        const float2 mul2 = make_float2(mul, mul);
 #pragma unroll
         for (int q4 = 0; q4 < 16; ++q4) {
           const float4 lv = l4[q4];
-          const float2 mul2 = make_float2(mul, mul);
           const float2 a01 = ffma2(make_float2(__uint_as_float(sr[q4 * 4 + 0]), __uint_as_float(sr[q4 * 4 + 1])), mul2,
                                    make_float2(-lv.x, -lv.y));
           const float2 a23 = ffma2(make_float2(__uint_as_float(sr[q4 * 4 + 2]), __uint_as_float(sr[q4 * 4 + 3])), mul2,
                                    make_float2(-lv.z, -lv.w));
-          const float p0 = fast_exp2(a01.x), p1 = fast_exp2(a01.y), p2 = fast_exp2(a23.x), p3 = fast_exp2(a23.y);
-          sr[q4 * 4 + 0] = __float_as_uint(p0);
-          sr[q4 * 4 + 1] = __float_as_uint(p1);
-          sr[q4 * 4 + 2] = __float_as_uint(p2);
-          sr[q4 * 4 + 3] = __float_as_uint(p3);
-          pw[q4 * 2] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
-          pw[q4 * 2 + 1] = BF16 ? pack_bf16x2(p2, p3) : pack_f16x2(p2, p3);
-        }
-        tmem_st32(x_tm, pw);  // P^T over the (already consumed) S^T block: frees the registers early
-        mbar_wait(&sm.dp_full[W], cnt & 1, 1404 + W);
-        tc_fence_after();
-        tmem_ld32(y_tm + 0, dp + 0);
-        tmem_ld32(y_tm + 32, dp + 32);
-        tc_wait_ld();
-#pragma unroll
-        for (int q4 = 0; q4 < 16; ++q4) {
-          const float4 dv = d4[q4];
-          const float2 t01 = fadd2(make_float2(__uint_as_float(dp[q4 * 4 + 0]), __uint_as_float(dp[q4 * 4 + 1])),
-                                   make_float2(-dv.x, -dv.y));
-          const float2 t23 = fadd2(make_float2(__uint_as_float(dp[q4 * 4 + 2]), __uint_as_float(dp[q4 * 4 + 3])),
-                                   make_float2(-dv.z, -dv.w));
-          const float2 e01 = fmul2(make_float2(__uint_as_float(sr[q4 * 4 + 0]), __uint_as_float(sr[q4 * 4 + 1])), t01);
-          const float2 e23 = fmul2(make_float2(__uint_as_float(sr[q4 * 4 + 2]), __uint_as_float(sr[q4 * 4 + 3])), t23);
-          dw[q4 * 2] = BF16 ? pack_bf16x2(e01.x, e01.y) : pack_f16x2(e01.x, e01.y);
-          dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(e23.x, e23.y) : pack_f16x2(e23.x, e23.y);
+          sr[q4 * 4 + 0] = __float_as_uint(fast_exp2(a01.x));
+          sr[q4 * 4 + 1] = __float_as_uint(fast_exp2(a01.y));
+          sr[q4 * 4 + 2] = __float_as_uint(fast_exp2(a23.x));
+          sr[q4 * 4 + 3] = __float_as_uint(fast_exp2(a23.y));
         }
       } else {
-        mbar_wait(&sm.dp_full[W], cnt & 1, 1404 + W);
-        tc_fence_after();
-        tmem_ld32(y_tm + 0, dp + 0);
-        tmem_ld32(y_tm + 32, dp + 32);
-        tc_wait_ld();
+        const int c0 = t.idx * 64;
         const int split = p.pos.seg_len - c0;
         const int a0 = p.pos.base0[t.owner] + p.pos.stride * c0 + p.q_pos_offset;
         const int a1 = p.pos.base1[t.owner] + p.pos.stride * (c0 - p.pos.seg_len) + p.q_pos_offset;
@@ -417,19 +408,16 @@ __device__ __forceinline__ void fz_softmax(FzSmem& sm, const AttnBwdFusedParams&
 #pragma unroll
         for (int q4 = 0; q4 < 16; ++q4) {
           const float4 lv = l4[q4];
-          const float4 dv = d4[q4];
           const float ls[4] = {lv.x, lv.y, lv.z, lv.w};
-          const float dl[4] = {dv.x, dv.y, dv.z, dv.w};
-          float pp[4], dd[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = q4 * 4 + e;
             const float sv = __uint_as_float(sr[j]);
-            float pj, chain = 1.f;
-            if (clamp) {
+            float pj;
+            if (CLAMP) {
               const float th = fast_tanh(sv * pre);
               pj = fast_exp2(fmaf(th, post, -ls[e]));
-              chain = 1.f - th * th;
+              ch[CLAMP ? j : 0] = 1.f - th * th;
             } else {
               pj = fast_exp2(fmaf(sv, mul, -ls[e]));
             }
@@ -442,19 +430,59 @@ __device__ __forceinline__ void fz_softmax(FzSmem& sm, const AttnBwdFusedParams&
                 if (p.window > 0) keep = keep && (pq - pos_k <= p.window);
               }
             }
-            if (!keep) pj = 0.f;
-            pp[e] = pj;
-            dd[e] = pj * (__uint_as_float(dp[j]) - dl[e]) * chain;
+            sr[j] = __float_as_uint(keep ? pj : 0.f);
           }
-          pw[q4 * 2] = BF16 ? pack_bf16x2(pp[0], pp[1]) : pack_f16x2(pp[0], pp[1]);
-          pw[q4 * 2 + 1] = BF16 ? pack_bf16x2(pp[2], pp[3]) : pack_f16x2(pp[2], pp[3]);
-          dw[q4 * 2] = BF16 ? pack_bf16x2(dd[0], dd[1]) : pack_f16x2(dd[0], dd[1]);
-          dw[q4 * 2 + 1] = BF16 ? pack_bf16x2(dd[2], dd[3]) : pack_f16x2(dd[2], dd[3]);
         }
-        tmem_st32(x_tm, pw);
       }
-      // P^T sits in X_w, dS^T goes over the consumed dP^T block Y_w (16-bit A operands of dV / dK) ...
-      tmem_st32(y_tm, dw);
+    };
+
+    // ---- A2: dP^T -> dS^T; hand P^T | dS^T to the acc issuer ----------------------------------------------------------
+    auto pass_a2 = [&](const uint32_t jj, uint32_t (&sr)[64], float (&ch)[CLAMP ? 64 : 1]) {
+      const uint32_t stg = (tile_base + jj) % QST;
+      const float4* d4 = reinterpret_cast<const float4*>(sm.delta[stg]);
+      uint32_t dw[32];
+      mbar_wait(&sm.dp_full[W], n_done & 1, 1404 + W);
+      tc_fence_after();
+      // Y_w holds dP^T (64 fp32 columns).  P^T (16 bit, 32 columns) may overwrite columns [0, 32) as soon as that half
+      // of dP^T sits in registers: two sequential half passes keep the live set small
+      // (the TMEM read port, shared with the other warpgroup's warp on this sub-partition, stays busy either way).
+      uint32_t dpa[32], dpb[32];
+      tmem_ld32(y_tm + 0, dpa);
+      {
+        uint32_t pw[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {  // pack P^T while dP^T is in flight
+          const float a = __uint_as_float(sr[2 * i]), b2 = __uint_as_float(sr[2 * i + 1]);
+          pw[i] = BF16 ? pack_bf16x2(a, b2) : pack_f16x2(a, b2);
+        }
+        tc_wait_ld();
+        tmem_st32(y_tm, pw);
+      }
+      auto half = [&](const uint32_t (&dp)[32], const int h0) {
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 dv = d4[h0 * 8 + q4];
+          const int j0 = h0 * 32 + q4 * 4;
+          const float2 t01 = fadd2(make_float2(__uint_as_float(dp[q4 * 4 + 0]), __uint_as_float(dp[q4 * 4 + 1])),
+                                   make_float2(-dv.x, -dv.y));
+          const float2 t23 = fadd2(make_float2(__uint_as_float(dp[q4 * 4 + 2]), __uint_as_float(dp[q4 * 4 + 3])),
+                                   make_float2(-dv.z, -dv.w));
+          float2 e01 = fmul2(make_float2(__uint_as_float(sr[j0 + 0]), __uint_as_float(sr[j0 + 1])), t01);
+          float2 e23 = fmul2(make_float2(__uint_as_float(sr[j0 + 2]), __uint_as_float(sr[j0 + 3])), t23);
+          if (CLAMP) {
+            e01 = fmul2(e01, make_float2(ch[CLAMP ? j0 + 0 : 0], ch[CLAMP ? j0 + 1 : 0]));
+            e23 = fmul2(e23, make_float2(ch[CLAMP ? j0 + 2 : 0], ch[CLAMP ? j0 + 3 : 0]));
+          }
+          dw[h0 * 16 + q4 * 2] = BF16 ? pack_bf16x2(e01.x, e01.y) : pack_f16x2(e01.x, e01.y);
+          dw[h0 * 16 + q4 * 2 + 1] = BF16 ? pack_bf16x2(e23.x, e23.y) : pack_f16x2(e23.x, e23.y);
+        }
+      };
+      half(dpa, 0);
+      tmem_ld32(y_tm + 32, dpb);
+      tc_wait_ld();
+      half(dpb, 1);
+      // dS^T next to P^T over the consumed dP^T block (16-bit A operands of dK / dV) ...
+      tmem_st32(y_tm + 32, dw);
       // ... and dS^T again as a shared-memory tile (B operand of dQ^T): row = key, 64 queries = 128 bytes, 128B swizzle
       // applied by hand (16-byte chunk c of row r sits at c ^ (r % 8)).  The rows of this warp alias its staging
       // buffer A: the TMA reductions that last read it must have finished reading.
@@ -471,16 +499,17 @@ __device__ __forceinline__ void fz_softmax(FzSmem& sm, const AttnBwdFusedParams&
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&sm.pds_ready[W]);
+    };
 
-      // drain dQ^T (lane = d, 64 query columns): registers -> [q][32 d] fp32 box per warp -> TMA reduce-add into the
-      // fp32 dQ accumulator ([b*h][n_pad][d]).  Two halves of 32 queries, staging B then A.
-      mbar_wait(&sm.dq_full[W], cnt & 1, 1408 + W);
+    // ---- drain: dQ^T (lane = d, 64 query columns) -> [q][32 d] fp32 box per warp -> TMA reduce-add --------------------
+    auto drain = [&](const ScanTile& t) {
+      mbar_wait(&sm.dq_full[W], n_done & 1, 1408 + W);
       tc_fence_after();
       const int head = t.rep * p.kv_heads + it.kvh;
-      const int row0 = (it.b * p.heads + head) * p.n_pad + c0;
+      const int row0 = (it.b * p.heads + head) * p.n_pad + t.idx * 64;
       {
         uint32_t g0[32];
-        tmem_ld32(x_tm + 0, g0);
+        tmem_ld32(y_tm + 0, g0);
         tc_wait_ld();
         float* dst = reinterpret_cast<float*>(buf_b) + lane;
 #pragma unroll
@@ -494,10 +523,10 @@ __device__ __forceinline__ void fz_softmax(FzSmem& sm, const AttnBwdFusedParams&
       }
       {
         uint32_t g1[32];
-        tmem_ld32(x_tm + 32, g1);
+        tmem_ld32(y_tm + 32, g1);
         tc_wait_ld();
         tc_fence_before();
-        mbar_arrive(&sm.x_free[W]);  // X_w may take S^T of this stream's next step now
+        mbar_arrive(&sm.y_free[W]);  // Y_w may take dP^T of this stream's next step now
         float* dst = reinterpret_cast<float*>(buf_a) + lane;
 #pragma unroll
         for (int qq = 0; qq < 32; ++qq) dst[qq * 32] = __uint_as_float(g1[qq]);
@@ -508,9 +537,25 @@ __device__ __forceinline__ void fz_softmax(FzSmem& sm, const AttnBwdFusedParams&
           bulk_commit();
         }
       }
-      cnt++;
+    };
+
+    ScanTile cur, nxt;
+    uint32_t jcur = 0, jnxt = 0;
+    uint32_t sr[64];              // probabilities of the step between its A1 and A2 passes
+    float ch[CLAMP ? 64 : 1];     // softclamp chain-rule factors (1 - tanh^2)
+    bool has = next_mine(cur, jcur);
+    if (has) pass_a1(cur, jcur, sr, ch);
+    while (has) {
+      const bool hasn = next_mine(nxt, jnxt);
+      pass_a2(jcur, sr, ch);                  // sr is dead afterwards ...
+      if (hasn) pass_a1(nxt, jnxt, sr, ch);   // ... and refilled while the tensor core runs dV / dK / dQ^T of step jcur
+      drain(cur);
+      n_done++;
+      cur = nxt;
+      jcur = jnxt;
+      has = hasn;
     }
-    tile_base += jn;  // both warpgroups walk the whole sequence, so the stage ring stays in step
+    tile_base += jn;
 
     // epilogue: warpgroup 0 owns dK, warpgroup 1 owns dV
     mbar_wait(&sm.acc_done, n_item & 1, 1410 + W);
@@ -590,7 +635,7 @@ __device__ __forceinline__ void fz_softmax(FzSmem& sm, const AttnBwdFusedParams&
   __syncwarp();
 }
 
-template <bool BF16, bool RING>
+template <bool BF16, bool RING, bool CLAMP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid_constant__ CUtensorMap map_kv,
                       const __grid_constant__ CUtensorMap map_dq, const __grid_constant__ AttnBwdFusedParams p) {
@@ -606,10 +651,11 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.s_full[i], 1);
+      mbar_init(&sm.s_free[i], 128);
       mbar_init(&sm.dp_full[i], 1);
       mbar_init(&sm.pds_ready[i], 128);
       mbar_init(&sm.dq_full[i], 1);
-      mbar_init(&sm.x_free[i], 128);
+      mbar_init(&sm.y_free[i], 128);
     }
     mbar_init(&sm.acc_done, 1);
     mbar_init(&sm.epi_done, 256);
@@ -631,11 +677,11 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_qd64, const __grid
   if (warp >= 8) {  // control warps on the highest warp ids: the scheduler favours them
     setmaxnreg_dec<120>();
     if (warp == 8) fz_producer(sm, p, &map_qd64, &map_kv);
-    if (warp == 9) fz_issue_s<BF16>(sm, p, tmem);
+    if (warp == 9) fz_issue_logits<BF16>(sm, p, tmem);
     if (warp == 10) fz_issue_acc<BF16>(sm, p, tmem);
   } else {
     setmaxnreg_inc<192>();
-    fz_softmax<BF16, RING>(sm, p, warp < 4 ? 0 : 1, tmem, &map_dq, p.map_dkv);
+    fz_softmax<BF16, RING, CLAMP>(sm, p, warp < 4 ? 0 : 1, tmem, &map_dq, p.map_dkv);
   }
   tc_fence_before();
   __syncthreads();
@@ -684,10 +730,15 @@ size_t attn_bwd_fused_smem_bytes() { return sizeof(FzSmem) + 1024; }
 void launch_attn_bwd_fused(const CUtensorMap& map_qd64, const CUtensorMap& map_kv, const CUtensorMap& map_dq,
                            const AttnBwdFusedParams& p, int num_sms, cudaStream_t stream) {
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnBwdFusedParams);
-  const bool ring = p.ring_reduce != 0;
+  const bool ring = p.ring_reduce != 0, clamp = p.softclamp > 0.f;
   Kern kern;
-  if (ring) kern = p.is_bf16 ? attn_bwd_fused_kernel<true, true> : attn_bwd_fused_kernel<false, true>;
-  else kern = p.is_bf16 ? attn_bwd_fused_kernel<true, false> : attn_bwd_fused_kernel<false, false>;
+  if (clamp) {
+    if (ring) kern = p.is_bf16 ? attn_bwd_fused_kernel<true, true, true> : attn_bwd_fused_kernel<false, true, true>;
+    else kern = p.is_bf16 ? attn_bwd_fused_kernel<true, false, true> : attn_bwd_fused_kernel<false, false, true>;
+  } else {
+    if (ring) kern = p.is_bf16 ? attn_bwd_fused_kernel<true, true, false> : attn_bwd_fused_kernel<false, true, false>;
+    else kern = p.is_bf16 ? attn_bwd_fused_kernel<true, false, false> : attn_bwd_fused_kernel<false, false, false>;
+  }
   const size_t smem = sizeof(FzSmem) + 1024;
   cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "bwd_fused smem attr");
   const int items = p.hop_count * p.batch * p.kv_heads * ((p.n_k + 127) / 128);

@@ -68,6 +68,11 @@ def test_fused_forward(name):
 
 BWD_CASES = {k: v for k, v in FWD_CASES.items() if k != "ring8_striped_causal"}
 BWD_CASES["n64_h1"] = dict(n=64, h=1)
+BWD_CASES["ring8_striped_causal_gqa"] = dict(world=8, n=512, h=8, hk=2, layout="striped", causal=True)
+# head dim 128 defaults to the one-kernel (5-GEMM) backward; the two-kernel pair stays covered explicitly
+BWD_CASES["two_kernel_d128_causal"] = dict(n=1000, causal=True, h=4, fused=False)
+BWD_CASES["two_kernel_gqa_causal"] = dict(n=512, h=8, hk=2, causal=True, fused=False)
+BWD_CASES["two_kernel_ring4_striped"] = dict(world=4, n=384, h=4, hk=2, layout="striped", causal=True, fused=False)
 
 
 @pytest.mark.parametrize("name", list(BWD_CASES))
@@ -144,12 +149,12 @@ def test_graft_smoke():
 # ------------------------------------------------------------------------------------------------
 # real multi-GPU ring (NVLink, symmetric memory) – needs >= 2 devices
 # ------------------------------------------------------------------------------------------------
-def _ring_worker(rank, world, layout, causal, hk, kmask=False, lean=False):
+def _ring_worker(rank, world, layout, causal, hk, kmask=False, backward="fused"):
     import torch.distributed as dist
 
     from ring_attention_pytorch_b200.ops import ring_cuda
 
-    ring_cuda.CONFIG["save_kv_gather"] = not lean
+    ring_cuda.CONFIG["backward"] = backward
 
     from ring_attention_pytorch_b200.ops.oracle import attention_with_positions
     from ring_attention_pytorch_b200.ops.ring_cuda import ring_flash_attn_cuda
@@ -189,19 +194,20 @@ def _ring_worker(rank, world, layout, causal, hk, kmask=False, lean=False):
     dist.barrier()
 
 
-@pytest.mark.parametrize("layout,causal,hk,kmask,lean", [("plain", False, 4, False, False),
-                                                         ("striped", True, 2, False, False),
-                                                         ("zigzag", True, 4, False, False),
-                                                         ("plain", False, 2, True, False),
-                                                         ("striped", True, 2, False, True)])
-def test_real_ring_two_gpus(layout, causal, hk, kmask, lean):
+@pytest.mark.parametrize("layout,causal,hk,kmask,backward", [("plain", False, 4, False, "fused"),
+                                                             ("striped", True, 2, False, "fused"),
+                                                             ("zigzag", True, 4, False, "fused"),
+                                                             ("plain", False, 2, True, "fused"),
+                                                             ("striped", True, 2, False, "two_kernel"),
+                                                             ("plain", False, 4, True, "two_kernel")])
+def test_real_ring_two_gpus(layout, causal, hk, kmask, backward):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     from dist_utils import run_distributed
 
     world = min(torch.cuda.device_count(), 8)
     world = 2 if world < 4 else 4
-    run_distributed(_ring_worker, world, layout, causal, hk, kmask, lean, backend="nccl")
+    run_distributed(_ring_worker, world, layout, causal, hk, kmask, backward, backend="nccl")
 
 
 # ------------------------------------------------------------------------------------------------
