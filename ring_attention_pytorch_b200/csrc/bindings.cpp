@@ -427,71 +427,82 @@ void acc_convert(const Tensor& acc, Tensor out, double scale) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// tree-attention decode
+// tree-attention decode: ONE persistent cooperative kernel (split-KV partials, in-kernel merge of the splits, publish,
+// cross-rank signal, merge over NVLink loads or NVLS multimem reductions).  Every buffer is owned by the caller
+// (ops/tree_decode_cuda.py caches them), so the call allocates nothing and can be captured in a CUDA graph.
 // ---------------------------------------------------------------------------------------------
-void tree_decode_partial(const Tensor& q, const c10::optional<Tensor>& k, const c10::optional<Tensor>& v,
-                         const c10::optional<Tensor>& k_scale, const c10::optional<Tensor>& v_scale, Tensor scratch,
-                         Tensor partial, int64_t kv_heads, int64_t splits, double scale, int64_t scale_block_keys) {
-  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kFloat && q.is_contiguous() && q.dim() == 3);
+int64_t tree_decode_max_ctas(int64_t d, int64_t kv_kind) { return rab::tree_decode_max_ctas((int)d, (int)kv_kind, sm_count()); }
+
+void tree_decode(const Tensor& q, const c10::optional<Tensor>& k, const c10::optional<Tensor>& v,
+                 const c10::optional<Tensor>& k_scale, const c10::optional<Tensor>& v_scale, Tensor scratch,
+                 Tensor group_done, Tensor counters, at::IntArrayRef partial_ptrs, int64_t aux_local_ptr,
+                 at::IntArrayRef pad_ptrs, int64_t mc_partial_ptr, int64_t mc_aux_ptr, int64_t rank, Tensor out,
+                 int64_t kv_heads, int64_t splits, double scale, int64_t scale_block_keys, double eps, int64_t grid) {
+  TORCH_CHECK(q.is_cuda() && q.is_contiguous() && q.dim() == 3, "q must be contiguous [b, h, d]");
   const int b = q.size(0), h = q.size(1), d = q.size(2);
   TORCH_CHECK(d == 64 || d == 128, "tree decode supports head dim 64 or 128");
-  TORCH_CHECK(partial.is_cuda() && partial.scalar_type() == at::kFloat && partial.is_contiguous() &&
-              partial.numel() >= (int64_t)b * h * (d + 2));
-  int n = 0, kind = 0;
-  const void* kp = nullptr;
-  const void* vp = nullptr;
+  rab::TreeDecodeParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.q = q.data_ptr();
+  p.q_kind = q.scalar_type() == at::kBFloat16 ? 0 : (q.scalar_type() == at::kHalf ? 1 : 2);
+  TORCH_CHECK(p.q_kind != 2 || q.scalar_type() == at::kFloat, "q must be bf16, fp16 or fp32");
+  int n = 0;
   if (k.has_value()) {
     TORCH_CHECK(v.has_value() && k->is_contiguous() && v->is_contiguous() && k->dim() == 4 && k->sizes() == v->sizes());
     TORCH_CHECK(k->size(0) == b && k->size(1) == kv_heads && k->size(3) == d);
     n = k->size(2);
-    if (k->scalar_type() == at::kBFloat16) kind = 0;
-    else if (k->scalar_type() == at::kHalf) kind = 1;
-    else if (k->scalar_type() == at::kFloat8_e4m3fn) kind = 2;
+    if (k->scalar_type() == at::kBFloat16) p.kv_kind = 0;
+    else if (k->scalar_type() == at::kHalf) p.kv_kind = 1;
+    else if (k->scalar_type() == at::kFloat8_e4m3fn) p.kv_kind = 2;
     else TORCH_CHECK(false, "k/v must be bf16, fp16 or float8_e4m3fn");
     TORCH_CHECK(v->scalar_type() == k->scalar_type());
-    kp = k->data_ptr();
-    vp = v->data_ptr();
+    p.k = k->data_ptr();
+    p.v = v->data_ptr();
   }
-  const float* ksp = nullptr;
-  const float* vsp = nullptr;
-  int n_scale_blocks = 1;
+  p.n_scale_blocks = 1;
+  p.scale_block = 1 << 30;  // per-head scales: the whole shard is one block
   if (k_scale.has_value()) {
     TORCH_CHECK(v_scale.has_value() && k_scale->sizes() == v_scale->sizes(), "k_scale and v_scale come together");
     TORCH_CHECK(k_scale->scalar_type() == at::kFloat && v_scale->scalar_type() == at::kFloat);
     TORCH_CHECK(k_scale->is_contiguous() && v_scale->is_contiguous() && k_scale->numel() % (b * kv_heads) == 0);
-    n_scale_blocks = k_scale->numel() / (b * kv_heads);
-    ksp = k_scale->data_ptr<float>();
-    vsp = v_scale->data_ptr<float>();
+    p.n_scale_blocks = k_scale->numel() / (b * kv_heads);
+    p.k_scale = k_scale->data_ptr<float>();
+    p.v_scale = v_scale->data_ptr<float>();
+    if (p.n_scale_blocks > 1) {
+      TORCH_CHECK(scale_block_keys > 0 && scale_block_keys % 64 == 0, "scale_block_keys must be a multiple of 64");
+      TORCH_CHECK((int64_t)p.n_scale_blocks * scale_block_keys >= n, "not enough scale blocks for the shard");
+      p.scale_block = (int)scale_block_keys;
+    }
   }
-  // keys per scale block: the whole shard for per-head scales, otherwise ceil(n / blocks) rounded to the 64-key tile
-  int scale_block = 1 << 30;
-  if (n_scale_blocks > 1) {
-    TORCH_CHECK(scale_block_keys > 0 && scale_block_keys % 64 == 0, "scale_block_keys must be a multiple of 64");
-    TORCH_CHECK((int64_t)n_scale_blocks * scale_block_keys >= n, "not enough scale blocks for the shard");
-    scale_block = (int)scale_block_keys;
-  }
+  p.batch = b; p.heads = h; p.kv_heads = (int)kv_heads; p.n = n; p.splits = (int)splits;
+  TORCH_CHECK(h % kv_heads == 0 && splits >= 1);
+  p.scale_log2 = (float)(scale * 1.4426950408889634);
+  const int g = h / (int)kv_heads;
   TORCH_CHECK(scratch.scalar_type() == at::kFloat && scratch.is_contiguous() &&
-              scratch.numel() >= (int64_t)b * kv_heads * splits * (h / kv_heads) * (d + 2));
-  c10::cuda::CUDAGuard guard(q.device());
-  rab::launch_tree_decode_partial(q.data_ptr<float>(), kp, vp, ksp, vsp, scratch.data_ptr<float>(),
-                                  partial.data_ptr<float>(), b, h, (int)kv_heads, n, d, (int)splits, kind,
-                                  (float)scale, scale_block, n_scale_blocks, at::cuda::getCurrentCUDAStream());
-}
-
-void tree_decode_reduce(at::IntArrayRef partial_ptrs, Tensor out, double eps) {
-  TORCH_CHECK(out.is_cuda() && out.is_contiguous() && out.dim() == 3);
-  const int bh = out.size(0) * out.size(1), d = out.size(2);
-  rab::TreeReduceParams p;
-  std::memset(&p, 0, sizeof(p));
+              scratch.numel() >= (int64_t)b * kv_heads * splits * g * (d + 4));
+  TORCH_CHECK(group_done.scalar_type() == at::kInt && group_done.numel() >= (int64_t)b * kv_heads * ((g + 3) / 4));
+  TORCH_CHECK(counters.scalar_type() == at::kInt && counters.numel() >= 4);
+  p.scratch = scratch.data_ptr<float>();
+  p.group_done = reinterpret_cast<uint32_t*>(group_done.data_ptr<int>());
+  p.counters = reinterpret_cast<uint32_t*>(counters.data_ptr<int>());
   p.world = (int)partial_ptrs.size();
-  TORCH_CHECK(p.world >= 1 && p.world <= rab::kMaxWorld);
-  for (int i = 0; i < p.world; ++i) p.partials[i] = reinterpret_cast<const float*>(partial_ptrs[i]);
+  p.rank = (int)rank;
+  TORCH_CHECK(p.world >= 1 && p.world <= rab::kMaxWorld && p.rank < p.world && (int)pad_ptrs.size() == p.world);
+  for (int i = 0; i < p.world; ++i) {
+    p.partials[i] = reinterpret_cast<const float*>(partial_ptrs[i]);
+    p.pads[i] = reinterpret_cast<uint32_t*>(pad_ptrs[i]);
+  }
+  p.partial_local = const_cast<float*>(p.partials[p.rank]);
+  p.aux_local = reinterpret_cast<float*>(aux_local_ptr);
+  p.mc_partial = reinterpret_cast<const float*>(mc_partial_ptr);
+  p.mc_aux = reinterpret_cast<const float*>(mc_aux_ptr);
+  TORCH_CHECK(out.is_cuda() && out.is_contiguous() && out.numel() == (int64_t)b * h * d);
   p.out = out.data_ptr();
-  p.out_is_bf16 = out.scalar_type() == at::kBFloat16 ? 1 : (out.scalar_type() == at::kHalf ? 0 : 2);
-  TORCH_CHECK(p.out_is_bf16 != 2 || out.scalar_type() == at::kFloat);
+  p.out_kind = out.scalar_type() == at::kBFloat16 ? 1 : (out.scalar_type() == at::kHalf ? 0 : 2);
+  TORCH_CHECK(p.out_kind != 2 || out.scalar_type() == at::kFloat);
   p.eps = (float)eps;
-  c10::cuda::CUDAGuard guard(out.device());
-  rab::launch_tree_decode_reduce(p, bh, d, at::cuda::getCurrentCUDAStream());
+  c10::cuda::CUDAGuard guard(q.device());
+  rab::launch_tree_decode(p, d, (int)grid, at::cuda::getCurrentCUDAStream());
 }
 
 void pack_kv(const Tensor& k, const Tensor& v, Tensor slot) {
@@ -569,9 +580,11 @@ TORCH_LIBRARY(rab, m) {
         "bool causal, int window, float scale, float softclamp, int pos_stride, int seg_len, int[] base0, int[] "
         "base1, int q_pos_offset, int[] hop_owner) -> (Tensor, Tensor)");
   m.def("pack_kv(Tensor k, Tensor v, Tensor(a!) slot) -> ()");
-  m.def("tree_decode_partial(Tensor q, Tensor? k, Tensor? v, Tensor? k_scale, Tensor? v_scale, Tensor(a!) scratch, "
-        "Tensor(b!) partial, int kv_heads, int splits, float scale, int scale_block_keys) -> ()");
-  m.def("tree_decode_reduce(int[] partial_ptrs, Tensor(a!) out, float eps) -> ()");
+  m.def("tree_decode(Tensor q, Tensor? k, Tensor? v, Tensor? k_scale, Tensor? v_scale, Tensor(a!) scratch, Tensor(b!) "
+        "group_done, Tensor(c!) counters, int[] partial_ptrs, int aux_local_ptr, int[] pad_ptrs, int mc_partial_ptr, int "
+        "mc_aux_ptr, int rank, Tensor(d!) out, int kv_heads, int splits, float scale, int scale_block_keys, float eps, "
+        "int grid) -> ()");
+  m.def("tree_decode_max_ctas(int d, int kv_kind) -> int");
   m.def("bwd_prep(Tensor q, Tensor o, Tensor dout, Tensor lse, Tensor(a!) qdo_buf, Tensor(b!) stat_buf, int rank) -> ()");
   m.def("attn_bwd_dq(Tensor qdo_buf, Tensor kv_buf, Tensor stat_buf, Tensor? ready, int ready_target, Tensor? "
         "kmask_bits, int batch, int heads, int kv_heads, int rank, bool causal, int window, float scale, float "
@@ -598,7 +611,7 @@ TORCH_LIBRARY_IMPL(rab, CUDA, m) {
   m.impl("umma_probe", &umma_probe);
   m.impl("attn_fwd", &attn_fwd);
   m.impl("pack_kv", &pack_kv);
-  m.impl("tree_decode_partial", &tree_decode_partial);
+  m.impl("tree_decode", &tree_decode);
   m.impl("bwd_prep", &bwd_prep);
   m.impl("attn_bwd_dq", &attn_bwd_dq);
   m.impl("attn_bwd_dkdv", &attn_bwd_dkdv);
@@ -612,7 +625,7 @@ TORCH_LIBRARY_IMPL(rab, CompositeExplicitAutograd, m) {
   m.impl("device_barrier", &device_barrier);
   m.impl("peer_copy", &peer_copy);
   m.impl("stream_write_u32", &stream_write_u32);
-  m.impl("tree_decode_reduce", &tree_decode_reduce);
+  m.impl("tree_decode_max_ctas", &tree_decode_max_ctas);
   m.impl("symm_alloc", &symm_alloc);
   m.impl("symm_open", &symm_open);
   m.impl("symm_close", &symm_close);

@@ -157,23 +157,36 @@ void launch_bwd_prep(const void* q, const void* o, const void* dout, const float
                      cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
-// tree-attention decode (tree_decode_sm100.cu)
+// tree-attention decode (tree_decode_sm100.cu): ONE persistent cooperative kernel per rank and step
 // ------------------------------------------------------------------------------------------------
-// q [b, h, d] fp32; k, v [b*hk, n, d] (kv_kind 0 bf16, 1 fp16, 2 fp8-e4m3); k_scale / v_scale: null or
-// [b*hk][n_scale_blocks] fp32 block scales, one per `scale_block` keys (scale_block % 64 == 0)
-// scratch [b*hk][splits][g][d+2] fp32; partial [b*h][d+2] fp32 = (out, lse*log2e, valid)
-void launch_tree_decode_partial(const float* q, const void* k, const void* v, const float* k_scale,
-                                const float* v_scale, float* scratch, float* partial, int batch, int heads,
-                                int kv_heads, int n, int d, int splits, int kv_kind, float scale, int scale_block,
-                                int n_scale_blocks, cudaStream_t stream);
-struct TreeReduceParams {
-  int world;
-  const float* partials[kMaxWorld];  // every rank's [b*h][d+2] partial (peer-mapped)
-  void* out;                         // [b*h][d]
-  int out_is_bf16;                   // 1 bf16, 0 fp16, 2 fp32
+struct TreeDecodeParams {
+  const void* q;            // [b, h, d]; q_kind 0 bf16, 1 fp16, 2 fp32
+  int q_kind;
+  const void* k;            // [b*hk, n, d]; kv_kind 0 bf16, 1 fp16, 2 fp8-e4m3
+  const void* v;
+  int kv_kind;
+  const float* k_scale;     // null or [b*hk][n_scale_blocks] fp32: one scale per `scale_block` keys (multiple of 64)
+  const float* v_scale;
+  int scale_block, n_scale_blocks;
+  int batch, heads, kv_heads, n, splits;
+  float scale_log2;         // softmax scale * log2(e)
+  float* scratch;           // [b*hk][splits][g][d+4] fp32 (used when splits > 1)
+  uint32_t* group_done;     // [b*hk*ceil(g/4)] zero-initialised, self-resetting
+  uint32_t* counters;       // [4] zero-initialised: queue head, grid-barrier count, grid-barrier generation, epoch
+  // cross-rank merge.  Row = (out[d], lse*log2e, valid, 0, 0); buffers hold TWO halves (alternating calls).
+  int world, rank;
+  float* partial_local;               // this rank's [2][b*h][d+4]
+  const float* partials[kMaxWorld];   // every rank's buffer (peer-mapped), index = rank
+  float* aux_local;                   // this rank's [2][2][b*h] (NVLS path: ordered-int lse, weights)
+  uint32_t* pads[kMaxWorld];          // signal pads: pads[r] lives on rank r, [2 rounds][kMaxWorld] words
+  const float* mc_partial;            // multicast (NVLS) mapping of the partial buffers, null -> P2P loads
+  const float* mc_aux;                // multicast mapping of the aux buffers
+  void* out;                          // [b*h][d]; out_kind 0 fp16, 1 bf16, 2 fp32
+  int out_kind;
   float eps;
 };
-void launch_tree_decode_reduce(const TreeReduceParams& p, int batch_heads, int d, cudaStream_t stream);
+int tree_decode_max_ctas(int d, int kv_kind, int num_sms);
+void launch_tree_decode(const TreeDecodeParams& p, int d, int grid, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // misc kernels (elementwise_sm100.cu)

@@ -1,15 +1,24 @@
-// Tree-attention decode for sm_100a: one query token per (batch, head) against a KV cache that is sharded
-// along the sequence across the ranks of one NVSwitch box.
+// Tree-attention decode for sm_100a: one query token per (batch, head) against a KV cache that is sharded along the
+// sequence across the ranks of one NVSwitch box — ONE persistent cooperative kernel per rank and step:
 //
-//   tree_decode_partial_kernel : split-KV flash-decoding over this rank's shard.  Bandwidth-bound, so it
-//       is a CUDA-core kernel tuned for coalesced 16-byte loads: one CTA per (split, batch*kv_head); the g
-//       query heads that share a KV head are processed together so K and V are read from HBM exactly once.
-//       KV may be bf16 / fp16 or fp8-e4m3 with per-(batch*kv_head) dequantisation scales (serve path).
-//   tree_decode_combine_kernel : merges the splits into this rank's (lse, out) partial and publishes it in
-//       the rank's symmetric (peer-mapped) slot.
-//   tree_decode_reduce_kernel  : after the device barrier, every rank reads all peers' partials straight
-//       over NVLink (P2P loads) and applies the max-rescale identity once -- replacing the reference's
-//       three latency-bound NCCL all-reduces (MAX lse, SUM den, SUM num; tree_attn_decoding.py:89-100).
+//   phase 1  split-KV flash decoding over this rank's shard.  Work units (batch*kv_head, group chunk, split) are handed
+//            out by an atomic queue to a grid of co-resident CTAs.  Bandwidth bound, so the inner loop is built around
+//            16-byte loads that are issued one tile AHEAD of their use (K of tile t+1 is in flight during the softmax and
+//            P V of tile t, V of tile t+1 during the scores of tile t+1) and the g query heads that share a KV head are
+//            processed together so K and V are read from HBM exactly once.  KV may be bf16 / fp16 or fp8-e4m3 with
+//            per-head or per-block dequantisation scales (serve path).  The CTA that finishes the LAST split of a group
+//            merges the splits and publishes (out, lse) in this rank's symmetric (peer-mapped) partial buffer.
+//   phase 2  grid barrier (all partials of this rank are published) -> one st.release.sys per peer on its signal pad,
+//            then every CTA waits until all peers have signalled this rank's pad (the pad is local memory).
+//   phase 3  cross-rank merge with the max-rescale identity, one warp per (batch, head) row:
+//              * P2P: every rank reads every peer's row straight over NVLink (W rows of d+2 floats), or
+//              * NVLS: multimem.ld_reduce through the multicast mapping of the partial buffers — the NVSwitch returns
+//                max_r(lse_r) and then sum_r(w_r out_r), sum_r(w_r) in two in-switch reductions.
+//
+// Replaces the reference's Triton launch padded to a 128-row tile plus three latency-bound NCCL all-reduces (MAX lse,
+// SUM den, SUM num; tree_attn_decoding.py:60-102).  All counters are self-resetting and the cross-rank epoch lives in
+// device memory, so the launch is CUDA-graph capturable; the host wrapper allocates nothing per call.
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 
@@ -21,15 +30,16 @@ namespace {
 
 constexpr int TD_THREADS = 128;
 constexpr int TD_TILE = 64;     // keys per inner tile
-constexpr int TD_MAX_G = 4;     // query heads per kv head handled by one CTA (larger groups use blockIdx.z)
+constexpr int TD_MAX_G = 4;     // query heads per kv head handled by one CTA (larger groups use more units)
 
+// ---- raw 16-byte (bf16 / fp16) or 8-byte (fp8) vectors of 8 elements -> fp32 ---------------------------------------
 template <int KV_KIND>  // 0 bf16, 1 fp16, 2 fp8 e4m3
-struct KvTraits;
+struct KvVec;
 template <>
-struct KvTraits<0> {
-  static constexpr int kElemsPer16B = 8;
-  __device__ static void load8(const void* p, float* out) {
-    const uint4 v = *reinterpret_cast<const uint4*>(p);
+struct KvVec<0> {
+  using Raw = uint4;
+  static constexpr int kBytes = 16;
+  __device__ static void cvt(const Raw& v, float* out) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -39,338 +49,524 @@ struct KvTraits<0> {
   }
 };
 template <>
-struct KvTraits<1> {
-  static constexpr int kElemsPer16B = 8;
-  __device__ static void load8(const void* p, float* out) {
-    const uint4 v = *reinterpret_cast<const uint4*>(p);
+struct KvVec<1> {
+  using Raw = uint4;
+  static constexpr int kBytes = 16;
+  __device__ static void cvt(const Raw& v, float* out) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
-      out[2 * i] = __low2float(h);
-      out[2 * i + 1] = __high2float(h);
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      out[2 * i] = f.x;
+      out[2 * i + 1] = f.y;
     }
   }
 };
 template <>
-struct KvTraits<2> {
-  __device__ static void load8(const void* p, float* out) {
-    const uint2 v = *reinterpret_cast<const uint2*>(p);  // 8 fp8 values
+struct KvVec<2> {
+  using Raw = uint2;
+  static constexpr int kBytes = 8;
+  __device__ static void cvt(const Raw& v, float* out) {
     const uint32_t w[2] = {v.x, v.y};
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const __nv_fp8x2_storage_t pair = (__nv_fp8x2_storage_t)((w[i] >> (16 * j)) & 0xffffu);
-        const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2(pair, __NV_E4M3);
-        const __half2 h = *reinterpret_cast<const __half2*>(&hr);
-        out[4 * i + 2 * j] = __low2float(h);
-        out[4 * i + 2 * j + 1] = __high2float(h);
+        // cvt.rn.f16x2.e4m3x2: two fp8 values per instruction, then one unpack per pair
+        const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((w[i] >> (16 * j)) & 0xffffu), __NV_E4M3);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hr));
+        out[4 * i + 2 * j] = f.x;
+        out[4 * i + 2 * j + 1] = f.y;
       }
     }
   }
 };
 
-template <int KV_KIND>
-__device__ __forceinline__ size_t kv_elem_bytes() {
-  return KV_KIND == 2 ? 1 : 2;
+__device__ __forceinline__ float load_q(const void* q, int kind, size_t idx) {
+  if (kind == 0) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(q)[idx]);
+  if (kind == 1) return __half2float(reinterpret_cast<const __half*>(q)[idx]);
+  return reinterpret_cast<const float*>(q)[idx];
 }
 
-// q: [b, h, d] (fp32 staged by the host wrapper), k: [b*hk, n, d], v: [b*hk, n, dv]
-// scratch: [b*hk][splits][g][dv + 2]  (acc..., m, l) in the log2 domain
-//
-// Per 64-key tile:   scores : 8 lanes per key, 4 keys per warp step, all 16-byte loads of the tile issued up
-//                             front (memory-level parallelism), q held in registers, 3-step shuffle reduce
-//                    softmax: warp gi owns head gi (online, log2 domain)
-//                    P V    : thread = (key group of 8, 8-column chunk); the 8 V loads of a tile are issued
-//                             before the FMAs; probabilities are broadcast from smem as one float4 per key
-template <int D, int KV_KIND>
-__global__ void __launch_bounds__(TD_THREADS)
-tree_decode_partial_kernel(const float* __restrict__ q, const void* __restrict__ k, const void* __restrict__ v,
-                           const float* __restrict__ k_scale, const float* __restrict__ v_scale,
-                           float* __restrict__ scratch, int heads, int kv_heads, int n, int splits,
-                           float scale_log2, int scale_block, int n_scale_blocks) {
-  const int g_total = heads / kv_heads;
-  const int g0 = blockIdx.z * TD_MAX_G;                 // first group member handled by this CTA
-  const int g = min(TD_MAX_G, g_total - g0);
-  const int bhk = blockIdx.y;
-  const int b = bhk / kv_heads, kvh = bhk % kv_heads;
-  const int split = blockIdx.x;
-  const int per = ((n + splits - 1) / splits + TD_TILE - 1) / TD_TILE * TD_TILE;  // tile-aligned splits
-  const int k0 = split * per, k1 = min(n, k0 + per);
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+// order-preserving map fp32 -> int32 (so that an integer max is the float max); used for the in-switch max
+__device__ __forceinline__ int float_to_ordered(float f) {
+  const int i = __float_as_int(f);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
-  __shared__ __align__(16) float s_s[TD_TILE][TD_MAX_G];  // scores, then probabilities: one float4 per key
-  __shared__ float corr_s[TD_MAX_G];
-  __shared__ float red_s[8][TD_MAX_G][D + 1];
+__device__ __forceinline__ float4 multimem_add_f32x4(const float* mc_addr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc_addr)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ float multimem_add_f32(const float* mc_addr) {
+  float r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(r) : "l"(mc_addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ int multimem_max_s32(const int* mc_addr) {
+  int r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.max.s32 %0, [%1];" : "=r"(r) : "l"(mc_addr) : "memory");
+  return r;
+}
 
-  // Block-scaled KV (fp8 serve path): one fp32 scale per `scale_block` keys of every (batch, kv head), applied to
-  // the scores (K) and folded into the probabilities (V).  scale_block is a multiple of the 64-key tile.
-  const float* ksb = k_scale ? k_scale + (size_t)bhk * n_scale_blocks : nullptr;
-  const float* vsb = v_scale ? v_scale + (size_t)bhk * n_scale_blocks : nullptr;
-
-  // QK ownership: 8 lanes per key (each lane D/8 elements), 4 keys per warp step, 16 keys per warp per tile
-  constexpr int EPL = D / 8;  // elements per lane: 16 (D=128) or 8 (D=64)
-  const int sub = lane / 8, l8 = lane % 8;
-  float2 qr[TD_MAX_G][EPL / 2];  // packed pairs: the dot products run on FFMA2
-#pragma unroll
-  for (int gi = 0; gi < TD_MAX_G; ++gi) {
-#pragma unroll
-    for (int e = 0; e < EPL / 2; ++e) {
-      // query head j uses kv head j % kv_heads  ->  heads {kvh, kvh + hk, ...}
-      const float* qp = q + ((size_t)b * heads + (g0 + gi) * kv_heads + kvh) * D + l8 * EPL + 2 * e;
-      qr[gi][e] = gi < g ? make_float2(qp[0] * scale_log2, qp[1] * scale_log2) : make_float2(0.f, 0.f);
-    }
-  }
-
-  // PV ownership: thread -> (key group kgrp, column chunk of 8 elements)
-  constexpr int CHUNKS = D / 8;                 // 16 for D=128, 8 for D=64
-  constexpr int KGROUPS = TD_THREADS / CHUNKS;  // 8 or 16
-  constexpr int KPT = TD_TILE / KGROUPS;        // keys per thread per tile: 8 or 4
-  const int chunk = tid % CHUNKS, kgrp = tid / CHUNKS;
-  float2 acc[TD_MAX_G][4];
-#pragma unroll
-  for (int gi = 0; gi < TD_MAX_G; ++gi)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc[gi][e] = make_float2(0.f, 0.f);
-  float m_run = -INFINITY, l_run = 0.f;  // warp gi keeps the running stats of head gi (identical in all lanes)
-
-  const size_t eb = kv_elem_bytes<KV_KIND>();
-  const uint8_t* kbase = reinterpret_cast<const uint8_t*>(k) + (size_t)bhk * n * D * eb;
-  const uint8_t* vbase = reinterpret_cast<const uint8_t*>(v) + (size_t)bhk * n * D * eb;
-
-  for (int t0 = k0; t0 < k1; t0 += TD_TILE) {
-    const float ks = ksb ? ksb[t0 / scale_block] : 1.f;
-    const float vs = vsb ? vsb[t0 / scale_block] : 1.f;
-    // ---- scores -------------------------------------------------------------------------------
-    float kf[4][EPL];
-#pragma unroll
-    for (int step = 0; step < 4; ++step) {
-      const int key = min(t0 + warp * 16 + step * 4 + sub, k1 - 1);  // clamp: loads stay in bounds
-      const uint8_t* row = kbase + ((size_t)key * D + l8 * EPL) * eb;
-#pragma unroll
-      for (int c = 0; c < EPL; c += 8) KvTraits<KV_KIND>::load8(row + c * eb, &kf[step][c]);
-    }
-#pragma unroll
-    for (int step = 0; step < 4; ++step) {
-      const int kl = warp * 16 + step * 4 + sub;
-      const bool live = (t0 + kl) < k1;
-      float part[TD_MAX_G];
-#pragma unroll
-      for (int gi = 0; gi < TD_MAX_G; ++gi) {
-        float2 a2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int e = 0; e < EPL / 2; ++e)
-          a2 = ffma2(make_float2(kf[step][2 * e], kf[step][2 * e + 1]), qr[gi][e], a2);
-        float a = a2.x + a2.y;
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2);
-        a += __shfl_xor_sync(0xffffffffu, a, 4);
-        part[gi] = live ? a * ks : -INFINITY;
-      }
-      if (l8 == 0) *reinterpret_cast<float4*>(&s_s[kl][0]) = make_float4(part[0], part[1], part[2], part[3]);
-    }
-    __syncthreads();
-    // ---- online softmax: warp gi owns head gi -------------------------------------------------------
-    if (warp < g) {
-      const int gi = warp;
-      const float a = s_s[lane][gi], bb = s_s[lane + 32][gi];
-      float mx = fmaxf(a, bb);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float m_prev = m_run, l_prev = l_run;
-      const float m_new = fmaxf(m_prev, mx);
-      const float m_eff = m_new == -INFINITY ? 0.f : m_new;
-      const float pa = fast_exp2(a - m_eff), pb = fast_exp2(bb - m_eff);
-      float sum = pa + pb;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float corr = m_prev == -INFINITY ? 0.f : fast_exp2(m_prev - m_eff);
-      s_s[lane][gi] = pa * vs;  // V block scale rides on the probabilities (the denominator uses the unscaled p)
-      s_s[lane + 32][gi] = pb * vs;
-      m_run = m_new;
-      l_run = l_prev * corr + sum;
-      if (lane == 0) corr_s[gi] = corr;
-    } else if (warp < TD_MAX_G) {
-      // unused head slots must read as zero probability in the float4 broadcast below
-      s_s[lane][warp] = 0.f;
-      s_s[lane + 32][warp] = 0.f;
-      if (lane == 0) corr_s[warp] = 0.f;
-    }
-    __syncthreads();
-    // ---- P V --------------------------------------------------------------------------------------
-    float vf[KPT][8];
-#pragma unroll
-    for (int i = 0; i < KPT; ++i) {
-      const int key = min(t0 + kgrp + i * KGROUPS, k1 - 1);
-      KvTraits<KV_KIND>::load8(vbase + ((size_t)key * D + chunk * 8) * eb, vf[i]);
-    }
-#pragma unroll
-    for (int gi = 0; gi < TD_MAX_G; ++gi) {
-      const float c = corr_s[gi];
-      const float2 c2 = make_float2(c, c);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[gi][e] = fmul2(acc[gi][e], c2);
-    }
-#pragma unroll
-    for (int i = 0; i < KPT; ++i) {
-      const int kl = kgrp + i * KGROUPS;
-      const float4 p4 = *reinterpret_cast<const float4*>(&s_s[kl][0]);  // 0 for keys beyond the shard
-      const float pk[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-      for (int gi = 0; gi < TD_MAX_G; ++gi) {
-        const float2 p2 = make_float2(pk[gi], pk[gi]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          acc[gi][e] = ffma2(p2, make_float2(vf[i][2 * e], vf[i][2 * e + 1]), acc[gi][e]);
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- reduce the key groups and write the split partial ------------------------------------------
-  float* out = scratch + (((size_t)bhk * splits + split) * g_total + g0) * (D + 2);
-  for (int gi = 0; gi < g; ++gi) {
-    if (kgrp < 8) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        red_s[kgrp][gi][chunk * 8 + 2 * e] = acc[gi][e].x;
-        red_s[kgrp][gi][chunk * 8 + 2 * e + 1] = acc[gi][e].y;
+// sense-reversing grid barrier on two words of device memory (all CTAs are co-resident: cooperative launch)
+__device__ __forceinline__ void grid_barrier(uint32_t* count, uint32_t* gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t my_gen = ld_acquire_gpu(gen);
+    __threadfence();
+    if (atomicAdd(count, 1u) == gridDim.x - 1) {
+      *count = 0;
+      __threadfence();
+      red_release_gpu_add(gen, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (ld_acquire_gpu(gen) == my_gen) {
+        if (clock64() - t0 > RAB_WATCHDOG_CYCLES) {
+          printf("[rab] tree decode grid barrier watchdog: block %d\n", (int)blockIdx.x);
+          __trap();
+        }
       }
     }
   }
   __syncthreads();
-  if (KGROUPS > 8) {  // D = 64: 16 key groups, fold the upper 8 onto the lower 8
+}
+
+template <int D, int KV_KIND>
+__global__ void __launch_bounds__(TD_THREADS)
+tree_decode_kernel(const __grid_constant__ TreeDecodeParams p) {
+  using Vec = KvVec<KV_KIND>;
+  using Raw = typename Vec::Raw;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int g_total = p.heads / p.kv_heads;
+  const int zchunks = (g_total + TD_MAX_G - 1) / TD_MAX_G;
+  const int groups = p.batch * p.kv_heads * zchunks;       // units = groups x splits
+  const int total_units = p.n > 0 ? groups * p.splits : 0;
+  constexpr int row_stride = D + 4;                         // (out[D], lse2, valid, pad, pad): rows stay 16-byte aligned
+  uint32_t* const ctr = p.counters;                         // [0] queue head, [1] barrier count, [2] barrier gen, [3] epoch
+  // The cross-rank epoch lives in device memory (graph replays advance it).  Calls alternate between two halves of
+  // the symmetric buffers: a half is rewritten two calls later, after every peer has signalled a round it can only
+  // reach once its reads of that half are complete.
+  const uint32_t base = ld_acquire_gpu(&ctr[3]);            // block 0 advances it behind the last grid barrier
+  const bool nvls_cfg = p.mc_partial != nullptr && p.world > 1;
+  const uint32_t call = nvls_cfg ? (base >> 1) : base;
+  const size_t half_off = (size_t)(call & 1u) * (size_t)p.batch * p.heads * row_stride;
+  const size_t aux_off = (size_t)(call & 1u) * (size_t)p.batch * p.heads * 2;
+  float* const my_partial = p.partial_local + half_off;
+  float* const my_aux = p.aux_local + aux_off;
+
+  __shared__ __align__(16) float s_s[2][TD_TILE][TD_MAX_G];  // scores, then probabilities (double buffered per tile)
+  __shared__ float corr_s[2][TD_MAX_G];
+  __shared__ float red_s[8][TD_MAX_G][D + 1];
+  __shared__ int unit_s;
+  __shared__ uint32_t last_s;
+  (void)my_aux;
+
+  constexpr int EPL = D / 8;                    // QK: 8 lanes per key, EPL elements per lane
+  constexpr int KVEC = EPL / 8;                 // 16-byte (8-byte for fp8) vectors per lane and key: 2 (D=128) or 1
+  constexpr int CHUNKS = D / 8;                 // PV: thread -> (key group, 8-column chunk)
+  constexpr int KGROUPS = TD_THREADS / CHUNKS;  // 8 or 16
+  constexpr int KPT = TD_TILE / KGROUPS;        // keys per thread per tile: 8 or 4
+  const int sub = lane / 8, l8 = lane % 8;
+  const int chunk = tid % CHUNKS, kgrp = tid / CHUNKS;
+  const size_t eb = KV_KIND == 2 ? 1 : 2;
+
+  // =========================================== phase 1: split-KV partials ============================================
+  while (true) {
+    if (tid == 0) unit_s = (int)atomicAdd(&ctr[0], 1u);
+    __syncthreads();
+    const int unit = unit_s;
+    __syncthreads();
+    if (unit >= total_units) break;
+    const int split = unit % p.splits;
+    const int grp = unit / p.splits;
+    const int zc = grp % zchunks;
+    const int bhk = grp / zchunks;
+    const int b = bhk / p.kv_heads, kvh = bhk % p.kv_heads;
+    const int g0 = zc * TD_MAX_G;
+    const int g = min(TD_MAX_G, g_total - g0);
+    const int per = ((p.n + p.splits - 1) / p.splits + TD_TILE - 1) / TD_TILE * TD_TILE;  // tile-aligned splits
+    const int k0 = split * per, k1 = min(p.n, k0 + per);
+
+    const float* ksb = p.k_scale ? p.k_scale + (size_t)bhk * p.n_scale_blocks : nullptr;
+    const float* vsb = p.v_scale ? p.v_scale + (size_t)bhk * p.n_scale_blocks : nullptr;
+    const uint8_t* kbase = reinterpret_cast<const uint8_t*>(p.k) + (size_t)bhk * p.n * D * eb;
+    const uint8_t* vbase = reinterpret_cast<const uint8_t*>(p.v) + (size_t)bhk * p.n * D * eb;
+
+    float2 qr[TD_MAX_G][EPL / 2];  // packed pairs: the dot products run on FFMA2
+#pragma unroll
+    for (int gi = 0; gi < TD_MAX_G; ++gi) {
+#pragma unroll
+      for (int e = 0; e < EPL / 2; ++e) {
+        // query head j uses kv head j % kv_heads  ->  heads {kvh, kvh + hk, ...}
+        const size_t qi = ((size_t)b * p.heads + (size_t)(g0 + gi) * p.kv_heads + kvh) * D + l8 * EPL + 2 * e;
+        qr[gi][e] = gi < g ? make_float2(load_q(p.q, p.q_kind, qi) * p.scale_log2, load_q(p.q, p.q_kind, qi + 1) * p.scale_log2)
+                           : make_float2(0.f, 0.f);
+      }
+    }
+    float2 acc[TD_MAX_G][4];
+#pragma unroll
+    for (int gi = 0; gi < TD_MAX_G; ++gi)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[gi][e] = make_float2(0.f, 0.f);
+    float m_run = -INFINITY, l_run = 0.f;  // warp gi keeps the running stats of head gi (identical in all lanes)
+
+    Raw kraw[4][KVEC], vraw[KPT];
+    auto load_k = [&](int t0) {
+#pragma unroll
+      for (int step = 0; step < 4; ++step) {
+        const int key = min(t0 + warp * 16 + step * 4 + sub, k1 - 1);  // clamp: loads stay in bounds
+        const uint8_t* row = kbase + ((size_t)key * D + l8 * EPL) * eb;
+#pragma unroll
+        for (int c = 0; c < KVEC; ++c) kraw[step][c] = *reinterpret_cast<const Raw*>(row + c * Vec::kBytes);
+      }
+    };
+    auto load_v = [&](int t0) {
+#pragma unroll
+      for (int i = 0; i < KPT; ++i) {
+        const int key = min(t0 + kgrp + i * KGROUPS, k1 - 1);
+        vraw[i] = *reinterpret_cast<const Raw*>(vbase + ((size_t)key * D + chunk * 8) * eb);
+      }
+    };
+    if (k0 < k1) {
+      load_k(k0);
+      load_v(k0);
+    }
+    uint32_t par = 0;
+    for (int t0 = k0; t0 < k1; t0 += TD_TILE, par ^= 1u) {
+      const float ks = ksb ? ksb[t0 / p.scale_block] : 1.f;
+      const float vs = vsb ? vsb[t0 / p.scale_block] : 1.f;
+      const bool more = t0 + TD_TILE < k1;
+      // ---- scores: consumes kraw ---------------------------------------------------------------------------------
+#pragma unroll
+      for (int step = 0; step < 4; ++step) {
+        float kf[EPL];
+#pragma unroll
+        for (int c = 0; c < KVEC; ++c) Vec::cvt(kraw[step][c], kf + 8 * c);
+        const int kl = warp * 16 + step * 4 + sub;
+        const bool live = (t0 + kl) < k1;
+        float part[TD_MAX_G];
+#pragma unroll
+        for (int gi = 0; gi < TD_MAX_G; ++gi) {
+          float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < EPL / 2; ++e) a2 = ffma2(make_float2(kf[2 * e], kf[2 * e + 1]), qr[gi][e], a2);
+          float a = a2.x + a2.y;
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2);
+          a += __shfl_xor_sync(0xffffffffu, a, 4);
+          part[gi] = live ? a * ks : -INFINITY;
+        }
+        if (l8 == 0) *reinterpret_cast<float4*>(&s_s[par][kl][0]) = make_float4(part[0], part[1], part[2], part[3]);
+      }
+      if (more) load_k(t0 + TD_TILE);  // in flight during the softmax and P V of this tile
+      __syncthreads();
+      // ---- online softmax: warp gi owns head gi ----------------------------------------------------------------
+      if (warp < g) {
+        const int gi = warp;
+        const float a = s_s[par][lane][gi], bb = s_s[par][lane + 32][gi];
+        float mx = fmaxf(a, bb);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float m_prev = m_run, l_prev = l_run;
+        const float m_new = fmaxf(m_prev, mx);
+        const float m_eff = m_new == -INFINITY ? 0.f : m_new;
+        const float pa = fast_exp2(a - m_eff), pb = fast_exp2(bb - m_eff);
+        float sum = pa + pb;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float corr = m_prev == -INFINITY ? 0.f : fast_exp2(m_prev - m_eff);
+        s_s[par][lane][gi] = pa * vs;  // V block scale rides on the probabilities (the denominator uses the unscaled p)
+        s_s[par][lane + 32][gi] = pb * vs;
+        m_run = m_new;
+        l_run = l_prev * corr + sum;
+        if (lane == 0) corr_s[par][gi] = corr;
+      } else if (warp < TD_MAX_G) {
+        // unused head slots must read as zero probability in the float4 broadcast below
+        s_s[par][lane][warp] = 0.f;
+        s_s[par][lane + 32][warp] = 0.f;
+        if (lane == 0) corr_s[par][warp] = 0.f;
+      }
+      __syncthreads();
+      // ---- P V: consumes vraw ---------------------------------------------------------------------------------------
+#pragma unroll
+      for (int gi = 0; gi < TD_MAX_G; ++gi) {
+        const float c = corr_s[par][gi];
+        const float2 c2 = make_float2(c, c);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[gi][e] = fmul2(acc[gi][e], c2);
+      }
+#pragma unroll
+      for (int i = 0; i < KPT; ++i) {
+        float vf[8];
+        Vec::cvt(vraw[i], vf);
+        const int kl = kgrp + i * KGROUPS;
+        const float4 p4 = *reinterpret_cast<const float4*>(&s_s[par][kl][0]);  // 0 for keys beyond the shard
+        const float pk[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+        for (int gi = 0; gi < TD_MAX_G; ++gi) {
+          const float2 p2 = make_float2(pk[gi], pk[gi]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[gi][e] = ffma2(p2, make_float2(vf[2 * e], vf[2 * e + 1]), acc[gi][e]);
+        }
+      }
+      if (more) load_v(t0 + TD_TILE);  // in flight during the scores and the softmax of the next tile
+      // no barrier here: the next tile writes the OTHER s_s / corr_s buffer; this one is rewritten two tiles later,
+      // behind the two barriers of the next tile
+    }
+
+    // ---- reduce the key groups, write the split result ----------------------------------------------------------------
+    __syncthreads();
     for (int gi = 0; gi < g; ++gi) {
-      if (kgrp >= 8) {
+      if (kgrp < 8) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          atomicAdd(&red_s[kgrp - 8][gi][chunk * 8 + 2 * e], acc[gi][e].x);
-          atomicAdd(&red_s[kgrp - 8][gi][chunk * 8 + 2 * e + 1], acc[gi][e].y);
+          red_s[kgrp][gi][chunk * 8 + 2 * e] = acc[gi][e].x;
+          red_s[kgrp][gi][chunk * 8 + 2 * e + 1] = acc[gi][e].y;
+        }
+      }
+    }
+    __syncthreads();
+    if (KGROUPS > 8) {  // D = 64: 16 key groups, fold the upper 8 onto the lower 8
+      for (int gi = 0; gi < g; ++gi) {
+        if (kgrp >= 8) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            atomicAdd(&red_s[kgrp - 8][gi][chunk * 8 + 2 * e], acc[gi][e].x);
+            atomicAdd(&red_s[kgrp - 8][gi][chunk * 8 + 2 * e + 1], acc[gi][e].y);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (p.splits == 1) {
+      // the unit IS the group: normalise and publish (out, lse2, valid) for its g heads directly
+      if (warp < g && lane == 0) {
+        corr_s[0][warp] = l_run > 0.f ? 1.f / l_run : 0.f;
+        const int head = (g0 + warp) * p.kv_heads + kvh;
+        float* row = my_partial + ((size_t)b * p.heads + head) * row_stride;
+        row[D] = l_run > 0.f ? (m_run == -INFINITY ? 0.f : m_run) + log2f(l_run) : -INFINITY;
+        row[D + 1] = l_run > 0.f ? 1.f : 0.f;
+      }
+      __syncthreads();
+      for (int i = tid; i < g * D; i += TD_THREADS) {
+        const int gi = i / D, c = i % D;
+        float sacc = 0.f;
+#pragma unroll
+        for (int kg = 0; kg < 8; ++kg) sacc += red_s[kg][gi][c];
+        const int head = (g0 + gi) * p.kv_heads + kvh;
+        my_partial[((size_t)b * p.heads + head) * row_stride + c] = sacc * corr_s[0][gi];
+      }
+    } else {
+      float* out = p.scratch + (((size_t)bhk * p.splits + split) * g_total + g0) * row_stride;
+      for (int i = tid; i < g * D; i += TD_THREADS) {
+        const int gi = i / D, c = i % D;
+        float sacc = 0.f;
+#pragma unroll
+        for (int kg = 0; kg < 8; ++kg) sacc += red_s[kg][gi][c];
+        out[gi * row_stride + c] = sacc;
+      }
+      if (warp < g && lane == 0) {
+        out[warp * row_stride + D] = m_run;
+        out[warp * row_stride + D + 1] = l_run;
+      }
+      // the CTA that completes the last split of the group merges the splits
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t done = atomicAdd(&p.group_done[grp], 1u);
+        last_s = (done == (uint32_t)p.splits - 1) ? 1u : 0u;
+        if (last_s) p.group_done[grp] = 0;  // self-resetting
+      }
+      __syncthreads();
+      if (last_s) {
+        __threadfence();
+        for (int gi = 0; gi < g; ++gi) {
+          const float* base = p.scratch + ((size_t)bhk * p.splits * g_total + g0 + gi) * row_stride;
+          const size_t stride = (size_t)g_total * row_stride;
+          float m = -INFINITY;
+          for (int s = 0; s < p.splits; ++s) m = fmaxf(m, __ldcg(&base[s * stride + D]));
+          const float m_eff = m == -INFINITY ? 0.f : m;
+          float l = 0.f;
+          for (int s = 0; s < p.splits; ++s) {
+            const float ms = __ldcg(&base[s * stride + D]);
+            l += ms == -INFINITY ? 0.f : __ldcg(&base[s * stride + D + 1]) * fast_exp2(ms - m_eff);
+          }
+          const int head = (g0 + gi) * p.kv_heads + kvh;
+          float* row = my_partial + ((size_t)b * p.heads + head) * row_stride;
+          for (int c = tid; c < D; c += TD_THREADS) {
+            float a = 0.f;
+            for (int s = 0; s < p.splits; ++s) {
+              const float ms = __ldcg(&base[s * stride + D]);
+              if (ms != -INFINITY) a += __ldcg(&base[s * stride + c]) * fast_exp2(ms - m_eff);
+            }
+            row[c] = l > 0.f ? a / l : 0.f;
+          }
+          if (tid == 0) {
+            row[D] = l > 0.f ? m_eff + log2f(l) : -INFINITY;
+            row[D + 1] = l > 0.f ? 1.f : 0.f;
+          }
         }
       }
     }
     __syncthreads();
   }
-  for (int i = tid; i < g * D; i += TD_THREADS) {
-    const int gi = i / D, c = i % D;
-    float sacc = 0.f;
-#pragma unroll
-    for (int kg = 0; kg < 8; ++kg) sacc += red_s[kg][gi][c];
-    out[gi * (D + 2) + c] = sacc;
-  }
-  if (warp < g && lane == 0) {
-    out[warp * (D + 2) + D] = m_run;
-    out[warp * (D + 2) + D + 1] = l_run;
-  }
-}
-
-// scratch [b*hk][splits][g][D+2] -> partial [b*h][D+2] = (normalised out[D], lse2, valid)
-template <int D>
-__global__ void tree_decode_combine_kernel(const float* __restrict__ scratch, float* __restrict__ partial, int heads,
-                                           int kv_heads, int splits, int n) {
-  const int g = heads / kv_heads;
-  const int bh = blockIdx.x;  // b * heads + head
-  const int b = bh / heads, head = bh % heads;
-  const int kvh = head % kv_heads, gi = head / kv_heads;
-  const int bhk = b * kv_heads + kvh;
-  const float* base = scratch + (size_t)bhk * splits * g * (D + 2) + gi * (D + 2);
-  const size_t stride = (size_t)g * (D + 2);
-  float m = -INFINITY;
-  if (n > 0)
-    for (int s = 0; s < splits; ++s) m = fmaxf(m, base[s * stride + D]);
-  const float m_eff = m == -INFINITY ? 0.f : m;
-  float l = 0.f;
-  if (n > 0)
-    for (int s = 0; s < splits; ++s) {
-      const float ms = base[s * stride + D];
-      l += ms == -INFINITY ? 0.f : base[s * stride + D + 1] * fast_exp2(ms - m_eff);
+  if (total_units == 0) {  // this rank holds no keys: publish empty rows
+    for (int i = blockIdx.x * TD_THREADS + tid; i < p.batch * p.heads; i += gridDim.x * TD_THREADS) {
+      my_partial[(size_t)i * row_stride + D] = -INFINITY;
+      my_partial[(size_t)i * row_stride + D + 1] = 0.f;
     }
-  const int c = threadIdx.x;
-  if (c < D) {
-    float acc = 0.f;
-    if (n > 0)
-      for (int s = 0; s < splits; ++s) {
-        const float ms = base[s * stride + D];
-        if (ms != -INFINITY) acc += base[s * stride + c] * fast_exp2(ms - m_eff);
+  }
+
+  // ====================================== phase 2: everyone's partials are visible ====================================
+  __threadfence();
+  grid_barrier(&ctr[1], &ctr[2]);
+  const int rows = p.batch * p.heads;
+  const int gwarp = blockIdx.x * (TD_THREADS / 32) + warp, nwarps = gridDim.x * (TD_THREADS / 32);
+  const bool nvls = p.mc_partial != nullptr && p.world > 1;
+  int* const my_ord = reinterpret_cast<int*>(my_aux);  // [rows] order-preserving integer image of this rank's lse
+  float* const my_w = my_aux + rows;                    // [rows] weight of this rank (NVLS path)
+  if (nvls) {
+    for (int bh = gwarp * 32 + lane; bh < rows; bh += nwarps * 32)
+      my_ord[bh] = float_to_ordered(my_partial[(size_t)bh * row_stride + D]);
+    __threadfence();
+    grid_barrier(&ctr[1], &ctr[2]);
+  }
+  // One signal round: block 0 tells every peer "my rows of this epoch are complete", then every CTA waits until all
+  // peers have said the same on THIS rank's pad (local memory: polling it costs no NVLink traffic).
+  auto signal_round = [&](int round, uint32_t epoch) {
+    if (p.world <= 1) return;
+    if (blockIdx.x == 0 && tid < p.world && tid != p.rank) {
+      __threadfence_system();
+      st_release_sys(p.pads[tid] + round * kMaxWorld + p.rank, epoch);
+    }
+    if (tid < p.world && tid != p.rank) {
+      const uint32_t* mine = p.pads[p.rank] + round * kMaxWorld + tid;
+      const long long t0 = clock64();
+      while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+        if (clock64() - t0 > 8 * RAB_WATCHDOG_CYCLES) {
+          printf("[rab] tree decode: rank %d waiting for rank %d round %d epoch %u\n", p.rank, tid, round, epoch);
+          __trap();
+        }
       }
-    partial[(size_t)bh * (D + 2) + c] = l > 0.f ? acc / l : 0.f;
-  }
-  if (c == 0) {
-    partial[(size_t)bh * (D + 2) + D] = l > 0.f ? m_eff + log2f(l) : -INFINITY;  // lse in log2 units
-    partial[(size_t)bh * (D + 2) + D + 1] = l > 0.f ? 1.f : 0.f;
-  }
-}
-
-// Every rank reads every peer's [b*h][D+2] partial over NVLink and merges them:
-//   out = sum_r out_r * 2^(lse_r - M) / sum_r 2^(lse_r - M),  M = max_r lse_r
-template <int D>
-__global__ void tree_decode_reduce_kernel(const __grid_constant__ TreeReduceParams p) {
-  const int bh = blockIdx.x;
-  const int c = threadIdx.x;
-  float mx = -INFINITY;
-  for (int r = 0; r < p.world; ++r) mx = fmaxf(mx, p.partials[r][(size_t)bh * (D + 2) + D]);
-  const float m_eff = mx == -INFINITY ? 0.f : mx;
-  float den = 0.f, num = 0.f;
-  for (int r = 0; r < p.world; ++r) {
-    const float* row = p.partials[r] + (size_t)bh * (D + 2);
-    const float lse = row[D];
-    if (lse == -INFINITY) continue;
-    const float wgt = fast_exp2(lse - m_eff);
-    den += wgt;
-    if (c < D) num += wgt * row[c];
-  }
-  if (c < D) {
-    const float o = num / fmaxf(den, p.eps);
-    if (p.out_is_bf16 == 1) {
-      reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)bh * D + c] = __float2bfloat16(o);
-    } else if (p.out_is_bf16 == 0) {
-      reinterpret_cast<__half*>(p.out)[(size_t)bh * D + c] = __float2half(o);
-    } else {
-      reinterpret_cast<float*>(p.out)[(size_t)bh * D + c] = o;
     }
+    __syncthreads();
+  };
+  signal_round(0, base + 1);
+
+  // ================================================ phase 3: merge ====================================================
+  auto store_row = [&](int bh, int c, float4 o) {
+    if (p.out_kind == 2) {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)bh * D)[c] = o;
+    } else {
+      uint2 w;
+      w.x = p.out_kind == 1 ? pack_bf16x2(o.x, o.y) : pack_f16x2(o.x, o.y);
+      w.y = p.out_kind == 1 ? pack_bf16x2(o.z, o.w) : pack_f16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (size_t)bh * D)[c] = w;
+    }
+  };
+  const bool own = lane * 4 < D;  // one warp per row; lane c owns columns [4c, 4c + 4)
+  if (!nvls) {
+    // P2P: every rank reads every peer's row straight over NVLink
+    for (int bh = gwarp; bh < rows; bh += nwarps) {
+      float lse[kMaxWorld];
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int r = 0; r < p.world; ++r) {
+        lse[r] = (p.partials[r] + half_off)[(size_t)bh * row_stride + D];
+        mx = fmaxf(mx, lse[r]);
+      }
+      const float m_eff = mx == -INFINITY ? 0.f : mx;
+      float den = 0.f;
+      float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int r = 0; r < p.world; ++r) {
+        if (lse[r] == -INFINITY) continue;
+        const float wgt = fast_exp2(lse[r] - m_eff);
+        den += wgt;
+        if (own) {
+          const float4 x = reinterpret_cast<const float4*>(p.partials[r] + half_off + (size_t)bh * row_stride)[lane];
+          num.x += wgt * x.x; num.y += wgt * x.y; num.z += wgt * x.z; num.w += wgt * x.w;
+        }
+      }
+      if (own) {
+        const float inv = 1.f / fmaxf(den, p.eps);
+        store_row(bh, lane, make_float4(num.x * inv, num.y * inv, num.z * inv, num.w * inv));
+      }
+    }
+  } else {
+    // NVLS: the switch returns M = max_r lse_r (integer max of the order-preserving image); every rank rescales ITS
+    // rows in place by w_r = 2^(lse_r - M) and publishes w_r; after a second signal round the switch returns
+    // sum_r w_r out_r and sum_r w_r.
+    const int* mc_ord = reinterpret_cast<const int*>(p.mc_aux + aux_off);
+    for (int bh = gwarp; bh < rows; bh += nwarps) {
+      const float M = ordered_to_float(multimem_max_s32(mc_ord + bh));
+      const float m_eff = M == -INFINITY ? 0.f : M;
+      float* row = my_partial + (size_t)bh * row_stride;
+      const float l = row[D];
+      const float wgt = l == -INFINITY ? 0.f : fast_exp2(l - m_eff);
+      if (own) {
+        float4 x = reinterpret_cast<float4*>(row)[lane];
+        x.x *= wgt; x.y *= wgt; x.z *= wgt; x.w *= wgt;
+        reinterpret_cast<float4*>(row)[lane] = x;
+      }
+      if (lane == 0) my_w[bh] = wgt;
+    }
+    __threadfence();
+    grid_barrier(&ctr[1], &ctr[2]);
+    signal_round(1, base + 2);
+    const float* mc_w = p.mc_aux + aux_off + rows;
+    const float* mc_rows = p.mc_partial + half_off;
+    for (int bh = gwarp; bh < rows; bh += nwarps) {
+      const float den = multimem_add_f32(mc_w + bh);
+      if (own) {
+        const float4 num = multimem_add_f32x4(mc_rows + (size_t)bh * row_stride + lane * 4);
+        const float inv = 1.f / fmaxf(den, p.eps);
+        store_row(bh, lane, make_float4(num.x * inv, num.y * inv, num.z * inv, num.w * inv));
+      }
+    }
+  }
+  // every CTA is done with the queue and has used `base`: reset / advance them for the next launch (graph replay safe)
+  grid_barrier(&ctr[1], &ctr[2]);
+  if (blockIdx.x == 0 && tid == 0) {
+    ctr[0] = 0;
+    ctr[3] = base + (nvls ? 2u : 1u);
   }
 }
 
 }  // namespace
 
-void launch_tree_decode_partial(const float* q, const void* k, const void* v, const float* k_scale,
-                                const float* v_scale, float* scratch, float* partial, int batch, int heads,
-                                int kv_heads, int n, int d, int splits, int kv_kind, float scale, int scale_block,
-                                int n_scale_blocks, cudaStream_t stream) {
-  const float scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid(splits, batch * kv_heads, (heads / kv_heads + TD_MAX_G - 1) / TD_MAX_G);
-  if (n > 0) {
-#define RAB_TD_LAUNCH(DD, KK)                                                                                   \
-  tree_decode_partial_kernel<DD, KK><<<grid, TD_THREADS, 0, stream>>>(                                          \
-      q, k, v, k_scale, v_scale, scratch, heads, kv_heads, n, splits, scale_log2, scale_block, n_scale_blocks)
-    if (d == 128) {
-      if (kv_kind == 0) RAB_TD_LAUNCH(128, 0);
-      else if (kv_kind == 1) RAB_TD_LAUNCH(128, 1);
-      else RAB_TD_LAUNCH(128, 2);
-    } else {
-      if (kv_kind == 0) RAB_TD_LAUNCH(64, 0);
-      else if (kv_kind == 1) RAB_TD_LAUNCH(64, 1);
-      else RAB_TD_LAUNCH(64, 2);
-    }
-#undef RAB_TD_LAUNCH
-    cuda_check(cudaGetLastError(), "tree_decode_partial launch");
-  }
+int tree_decode_max_ctas(int d, int kv_kind, int num_sms) {
+  int per_sm = 0;
+  const void* fn = nullptr;
+#define RAB_TD_PICK(DD, KK) fn = (const void*)tree_decode_kernel<DD, KK>
   if (d == 128) {
-    tree_decode_combine_kernel<128><<<batch * heads, 128, 0, stream>>>(scratch, partial, heads, kv_heads, splits, n);
+    if (kv_kind == 0) RAB_TD_PICK(128, 0); else if (kv_kind == 1) RAB_TD_PICK(128, 1); else RAB_TD_PICK(128, 2);
   } else {
-    tree_decode_combine_kernel<64><<<batch * heads, 64, 0, stream>>>(scratch, partial, heads, kv_heads, splits, n);
+    if (kv_kind == 0) RAB_TD_PICK(64, 0); else if (kv_kind == 1) RAB_TD_PICK(64, 1); else RAB_TD_PICK(64, 2);
   }
-  cuda_check(cudaGetLastError(), "tree_decode_combine launch");
+#undef RAB_TD_PICK
+  cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, TD_THREADS, 0), "tree_decode occupancy");
+  return per_sm * num_sms;
 }
 
-void launch_tree_decode_reduce(const TreeReduceParams& p, int batch_heads, int d, cudaStream_t stream) {
+void launch_tree_decode(const TreeDecodeParams& p, int d, int grid, cudaStream_t stream) {
+  const void* fn = nullptr;
+#define RAB_TD_PICK(DD, KK) fn = (const void*)tree_decode_kernel<DD, KK>
   if (d == 128) {
-    tree_decode_reduce_kernel<128><<<batch_heads, 128, 0, stream>>>(p);
+    if (p.kv_kind == 0) RAB_TD_PICK(128, 0); else if (p.kv_kind == 1) RAB_TD_PICK(128, 1); else RAB_TD_PICK(128, 2);
   } else {
-    tree_decode_reduce_kernel<64><<<batch_heads, 64, 0, stream>>>(p);
+    if (p.kv_kind == 0) RAB_TD_PICK(64, 0); else if (p.kv_kind == 1) RAB_TD_PICK(64, 1); else RAB_TD_PICK(64, 2);
   }
-  cuda_check(cudaGetLastError(), "tree_decode_reduce launch");
+#undef RAB_TD_PICK
+  void* args[] = {(void*)&p};
+  // cooperative: the grid barrier and the cross-rank waits need every CTA of the grid to be resident
+  cuda_check(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(TD_THREADS), args, 0, stream), "tree_decode launch");
 }
 
 }  // namespace rab

@@ -3,10 +3,11 @@
 
 Layout is head-first like the reference: ``q [b, h, 1, d]``, ``k [b, hk, n, d]``, ``v [b, hk, n, dv]``.
 
-* CUDA path: ``csrc/tree_decode_sm100.cu`` – ONE kernel per rank computes the split-KV partial
-  (max, sum, out) for its KV shard, publishes it in symmetric memory and combines all ranks' partials
-  in-kernel over NVLink (one pass using the max-rescale identity), replacing the reference's Triton launch
-  padded to a 128-row tile plus three latency-bound all-reduces (MAX, SUM, SUM).
+* CUDA path: ``csrc/tree_decode_sm100.cu`` – ONE persistent cooperative kernel per rank and step computes the
+  split-KV partials of its KV shard, merges the splits, publishes ``(out, lse)`` in symmetric memory, signals the
+  peers and merges all ranks' partials in-kernel (NVLink peer loads, or ``multimem.ld_reduce`` through the NVSwitch
+  when the buffers have a multicast mapping), replacing the reference's Triton launch padded to a 128-row tile plus
+  three latency-bound all-reduces (MAX, SUM, SUM).
 * portable path (CPU / gloo): local einsum attention + one MAX and one packed SUM all-reduce.
 
 Fixes vs. the reference: ``shard_kv_seq=False`` with ``k=None`` works (reference uses an undefined ``dim_v``

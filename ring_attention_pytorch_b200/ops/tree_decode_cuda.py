@@ -1,22 +1,124 @@
-"""sm_100a tree-attention decode (see csrc/tree_decode_sm100.cu and ops/tree_decode.py)."""
+"""sm_100a tree-attention decode: ONE persistent cooperative kernel per rank and step (``csrc/tree_decode_sm100.cu``).
+
+The kernel computes the split-KV partials of this rank's shard, merges the splits, publishes ``(out, lse)`` in a
+symmetric buffer, signals the peers and merges all ranks' partials — over NVLink peer loads, or, when the buffers have a
+multicast (NVLS) mapping, with ``multimem.ld_reduce`` inside the NVSwitch.  This wrapper only owns the buffers: they are
+cached per (device, world, rows, head dim), every counter is self-resetting and the cross-rank epoch lives in device
+memory, so a decode step allocates nothing and is CUDA-graph capturable.  Reference: tree_attn_decoding.py:60-102 (one
+Triton launch padded to 128 rows + three all-reduces).
+"""
 from __future__ import annotations
 
-from typing import Optional
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
 
 import torch
+import torch.distributed as dist
 from torch import Tensor
 
 from ring_attention_pytorch_b200.ops import _ext
-from ring_attention_pytorch_b200.parallel.distributed import get_world_size, is_distributed
+from ring_attention_pytorch_b200.parallel.distributed import get_rank, get_world_size, is_distributed
 
 LAUNCHES = {"count": 0}
+# "auto": use the NVSwitch multicast mapping when torch's symmetric memory can provide one, else NVLink peer loads
+CONFIG = {"nvls": "auto"}
+K_MAX_WORLD = 16
+PAD_WORDS = 2 * K_MAX_WORLD  # two signal rounds
 
 
-def _choose_splits(n: int, ctas_per_split: int, sm_count: int = 148) -> int:
+def _choose_splits(n: int, groups: int, resident_ctas: int) -> int:
+    """Enough work units to fill the persistent grid about twice, at least 256 keys per split."""
     if n <= 0:
         return 1
-    want = max(1, (2 * sm_count + ctas_per_split - 1) // ctas_per_split)
+    want = max(1, (2 * resident_ctas + groups - 1) // groups)
     return max(1, min(want, (n + 255) // 256))
+
+
+@dataclass
+class _Buffers:
+    rows: int
+    d: int
+    world: int
+    rank: int
+    partial_ptrs: List[int]
+    aux_local_ptr: int
+    pad_ptrs: List[int]
+    mc_partial_ptr: int
+    mc_aux_ptr: int
+    counters: Tensor
+    keep: tuple  # owners of the memory above
+    scratch: Optional[Tensor] = None
+    group_done: Optional[Tensor] = None
+
+
+_cache: Dict[Tuple, _Buffers] = {}
+
+
+def _layout(rows: int, d: int) -> Tuple[int, int, int, int]:
+    """Byte offsets of (partials, aux, pads) inside one symmetric allocation and its total size."""
+    partial_bytes = 2 * rows * (d + 4) * 4
+    aux_bytes = 2 * 2 * rows * 4
+    pad_bytes = PAD_WORDS * 4
+    a = (partial_bytes + 255) // 256 * 256
+    b = a + (aux_bytes + 255) // 256 * 256
+    return 0, a, b, b + (pad_bytes + 255) // 256 * 256
+
+
+def _alloc_symmetric(nbytes: int, dev: torch.device, world: int, rank: int):
+    """(local uint8 tensor, per-rank base addresses, multicast base or 0, owner).  Tries torch's symmetric memory first
+    (it can bind the allocation to an NVSwitch multicast object); falls back to the package's own IPC regions."""
+    if world == 1:
+        t = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        return t, [t.data_ptr()], 0, t
+    if CONFIG["nvls"] in ("auto", True, "on"):
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            t = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+            hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+            t.zero_()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            return t, [int(x) for x in hdl.buffer_ptrs], mc, (t, hdl)
+        except Exception as e:  # noqa: BLE001 - no fabric / multicast support: plain peer mappings still work
+            if CONFIG["nvls"] in (True, "on"):
+                raise
+            _alloc_symmetric.last_error = f"{type(e).__name__}: {e}"
+    from ring_attention_pytorch_b200.parallel.symm import get_workspace
+
+    ws = get_workspace(world, dev)
+    reg = ws.region(f"tree_decode_{nbytes}", nbytes)
+    reg.local.zero_()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    return reg.local, list(reg.peer_ptrs), 0, reg
+
+
+_alloc_symmetric.last_error = None
+
+
+def _buffers(rows: int, d: int, dev: torch.device) -> _Buffers:
+    world = get_world_size() if is_distributed() else 1
+    rank = get_rank() if world > 1 else 0
+    key = (dev.index, world, rows, d)
+    buf = _cache.get(key)
+    if buf is None:
+        off_p, off_a, off_s, total = _layout(rows, d)
+        local, bases, mc, owner = _alloc_symmetric(total, dev, world, rank)
+        buf = _Buffers(rows=rows, d=d, world=world, rank=rank, partial_ptrs=[x + off_p for x in bases],
+                       aux_local_ptr=bases[rank] + off_a, pad_ptrs=[x + off_s for x in bases],
+                       mc_partial_ptr=(mc + off_p) if mc else 0, mc_aux_ptr=(mc + off_a) if mc else 0,
+                       counters=torch.zeros(4, dtype=torch.int32, device=dev), keep=(local, owner))
+        _cache[key] = buf
+    return buf
+
+
+def uses_nvls(q: Tensor) -> bool:
+    """True when the decode of this (shape, device) merges through the NVSwitch multicast mapping."""
+    b, h, _, d = q.shape
+    key = (q.device.index, get_world_size() if is_distributed() else 1, b * h, d)
+    return key in _cache and _cache[key].mc_partial_ptr != 0
 
 
 @torch.no_grad()
@@ -30,21 +132,25 @@ def tree_decode_cuda(
     k_scale: Optional[Tensor] = None,
     v_scale: Optional[Tensor] = None,
     scale_block_keys: int = 0,
+    out: Optional[Tensor] = None,
 ) -> Tensor:
-    """q [b, h, 1, d]; k, v [b, hk, n, d] this rank's shard (bf16 / fp16 / float8_e4m3fn) or None.
+    """q [b, h, 1, d] (bf16 / fp16 / fp32); k, v [b, hk, n, d] this rank's shard (bf16 / fp16 / float8_e4m3fn) or None.
 
     ``k_scale`` / ``v_scale``: optional fp32 dequantisation scales for the fp8 path, either per (batch, kv head)
     (``numel == b*hk``) or block-scaled ``[b*hk, n_blocks]`` with one scale per ``scale_block_keys`` keys
-    (a multiple of 64).
-    Returns [b, h, 1, d] in q's dtype (fp32 if q is fp32).
+    (a multiple of 64).  ``out`` ([b, h, 1, d]) may be passed to make the call allocation free (CUDA graphs).
+    Returns [b, h, 1, d] in q's dtype.
     """
     ops = _ext.ops()
     b, h, _, d = q.shape
     assert dim_v == d, "the decode kernel assumes dim_v == dim_qk"
     dev = q.device
-    qf = q.reshape(b, h, d).float().contiguous()
-    n = 0
-    hk = h
+    q3 = q.reshape(b, h, d)
+    if not q3.is_contiguous():
+        q3 = q3.contiguous()
+    if q3.dtype not in (torch.bfloat16, torch.float16, torch.float32):
+        q3 = q3.float()
+    n, hk = 0, h
     if k is not None and k.shape[-2] > 0:
         if k.dtype == torch.float32:
             k, v = k.to(torch.bfloat16), v.to(torch.bfloat16)
@@ -53,26 +159,23 @@ def tree_decode_cuda(
     else:
         k = v = None
     g = h // hk
-    zchunks = (g + 3) // 4
-    splits = _choose_splits(n, b * hk * zchunks)
-    scratch = torch.empty(b * hk * splits * g * (d + 2), dtype=torch.float32, device=dev)
-    out_dtype = q.dtype if q.dtype in (torch.bfloat16, torch.float16) else torch.float32
-    out = torch.empty(b, h, d, dtype=out_dtype, device=dev)
-    nbytes = b * h * (d + 2) * 4
-    scale = d ** -0.5
-    if is_distributed():
-        from ring_attention_pytorch_b200.parallel.symm import get_workspace
-
-        ws = get_workspace(get_world_size(), dev)
-        stage, peer_ptrs = ws.staging("tree_partial", nbytes)
-        partial = stage.view(torch.float32)
-        ops.tree_decode_partial(qf, k, v, k_scale, v_scale, scratch, partial, hk, splits, scale, scale_block_keys)
-        ws.barrier()
-        ops.tree_decode_reduce(peer_ptrs, out, eps)
-        LAUNCHES["count"] += 4 if n > 0 else 3
-    else:
-        partial = torch.empty(b * h * (d + 2), dtype=torch.float32, device=dev)
-        ops.tree_decode_partial(qf, k, v, k_scale, v_scale, scratch, partial, hk, splits, scale, scale_block_keys)
-        ops.tree_decode_reduce([partial.data_ptr()], out, eps)
-        LAUNCHES["count"] += 3 if n > 0 else 2
-    return out.view(b, h, 1, d)
+    groups = b * hk * ((g + 3) // 4)
+    kv_kind = 0 if k is None or k.dtype == torch.bfloat16 else (1 if k.dtype == torch.float16 else 2)
+    resident = int(ops.tree_decode_max_ctas(d, kv_kind))
+    splits = _choose_splits(n, groups, resident)
+    buf = _buffers(b * h, d, dev)
+    need = b * hk * splits * g * (d + 4)
+    if buf.scratch is None or buf.scratch.numel() < need:
+        buf.scratch = torch.empty(need, dtype=torch.float32, device=dev)
+    if buf.group_done is None or buf.group_done.numel() < groups:
+        buf.group_done = torch.zeros(groups, dtype=torch.int32, device=dev)
+    if out is None:
+        out_dtype = q.dtype if q.dtype in (torch.bfloat16, torch.float16) else torch.float32
+        out = torch.empty(b, h, 1, d, dtype=out_dtype, device=dev)
+    units = groups * splits if n > 0 else 0
+    grid = max(1, min(resident, max(units, (b * h + 3) // 4)))
+    ops.tree_decode(q3, k, v, k_scale, v_scale, buf.scratch, buf.group_done, buf.counters, buf.partial_ptrs,
+                    buf.aux_local_ptr, buf.pad_ptrs, buf.mc_partial_ptr, buf.mc_aux_ptr, buf.rank, out.view(b, h, d), hk,
+                    splits, d ** -0.5, scale_block_keys, eps, grid)
+    LAUNCHES["count"] += 1
+    return out
