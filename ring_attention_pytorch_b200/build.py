@@ -32,6 +32,7 @@ CU_SOURCES = [
     "attn_bwd_sm100.cu",
     "attn_bwd_fused_sm100.cu",
     "tree_decode_sm100.cu",
+    "tree_decode_tc_sm100.cu",
     "elementwise_sm100.cu",
 ]
 CPP_SOURCES = ["tmap.cpp", "symm.cpp"]

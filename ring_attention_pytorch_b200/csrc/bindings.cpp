@@ -431,13 +431,17 @@ void acc_convert(const Tensor& acc, Tensor out, double scale) {
 // cross-rank signal, merge over NVLink loads or NVLS multimem reductions).  Every buffer is owned by the caller
 // (ops/tree_decode_cuda.py caches them), so the call allocates nothing and can be captured in a CUDA graph.
 // ---------------------------------------------------------------------------------------------
-int64_t tree_decode_max_ctas(int64_t d, int64_t kv_kind) { return rab::tree_decode_max_ctas((int)d, (int)kv_kind, sm_count()); }
+int64_t tree_decode_max_ctas(int64_t d, int64_t kv_kind, bool tensor_core) {
+  if (tensor_core) return rab::tree_decode_tc_max_ctas((int)kv_kind, sm_count());
+  return rab::tree_decode_max_ctas((int)d, (int)kv_kind, sm_count());
+}
 
 void tree_decode(const Tensor& q, const c10::optional<Tensor>& k, const c10::optional<Tensor>& v,
                  const c10::optional<Tensor>& k_scale, const c10::optional<Tensor>& v_scale, Tensor scratch,
                  Tensor group_done, Tensor counters, at::IntArrayRef partial_ptrs, int64_t aux_local_ptr,
                  at::IntArrayRef pad_ptrs, int64_t mc_partial_ptr, int64_t mc_aux_ptr, int64_t rank, Tensor out,
-                 int64_t kv_heads, int64_t splits, double scale, int64_t scale_block_keys, double eps, int64_t grid) {
+                 int64_t kv_heads, int64_t splits, double scale, int64_t scale_block_keys, double eps, int64_t grid,
+                 bool tensor_core) {
   TORCH_CHECK(q.is_cuda() && q.is_contiguous() && q.dim() == 3, "q must be contiguous [b, h, d]");
   const int b = q.size(0), h = q.size(1), d = q.size(2);
   TORCH_CHECK(d == 64 || d == 128, "tree decode supports head dim 64 or 128");
@@ -502,10 +506,26 @@ void tree_decode(const Tensor& q, const c10::optional<Tensor>& k, const c10::opt
   TORCH_CHECK(p.out_kind != 2 || out.scalar_type() == at::kFloat);
   p.eps = (float)eps;
   c10::cuda::CUDAGuard guard(q.device());
-  rab::launch_tree_decode(p, d, (int)grid, at::cuda::getCurrentCUDAStream());
+  if (tensor_core) {
+    TORCH_CHECK(d == 128 && n > 0, "the tcgen05 decode kernel needs head dim 128 and a non-empty shard");
+    // K, V [b*hk, n, d] -> dims (d, n, b*hk); box = one 128-byte wide, 128-key sub-tile
+    const uint64_t eb = p.kv_kind == 2 ? 1 : 2;
+    uint64_t dims[3] = {(uint64_t)d, (uint64_t)n, (uint64_t)b * kv_heads};
+    uint64_t strides[2] = {(uint64_t)d * eb, (uint64_t)n * d * eb};
+    uint32_t box[3] = {(uint32_t)(128 / eb), 128, 1};
+    auto mk = [&](const void* base) {
+      if (p.kv_kind == 2) return rab::make_tmap_u8(base, 3, dims, strides, box, rab::TmapSwizzle::B128);
+      if (p.kv_kind == 1) return rab::make_tmap_f16(base, 3, dims, strides, box, rab::TmapSwizzle::B128);
+      return rab::make_tmap_bf16(base, 3, dims, strides, box, rab::TmapSwizzle::B128);
+    };
+    CUtensorMap map_k = mk(p.k), map_v = mk(p.v);
+    rab::launch_tree_decode_tc(map_k, map_v, p, (int)grid, at::cuda::getCurrentCUDAStream());
+  } else {
+    rab::launch_tree_decode(p, d, (int)grid, at::cuda::getCurrentCUDAStream());
+  }
 }
 
-void pack_kv(const Tensor& k, const Tensor& v, Tensor slot) {
+void pack_kv(const Tensor& k, const Tensor& v, Tensor slot, int64_t which) {
   check_16bit(k, "k");
   check_16bit(v, "v");
   TORCH_CHECK(k.dim() == 4 && v.dim() == 4 && k.sizes() == v.sizes());
@@ -516,8 +536,31 @@ void pack_kv(const Tensor& k, const Tensor& v, Tensor slot) {
     TORCH_CHECK(k.stride(i) % 8 == 0 && v.stride(i) % 8 == 0, "k/v strides must be multiples of 8 elements");
   TORCH_CHECK(slot.is_contiguous() && slot.numel() == 2ll * b * n * hk * d && slot.scalar_type() == k.scalar_type());
   c10::cuda::CUDAGuard guard(k.device());
+  TORCH_CHECK(which >= 1 && which <= 3, "which: 1 = K half, 2 = V half, 3 = both");
   rab::launch_pack_kv(k.data_ptr(), v.data_ptr(), slot.data_ptr(), b, n, hk, d, k.stride(0), k.stride(1), k.stride(2),
-                      v.stride(0), v.stride(1), v.stride(2), at::cuda::getCurrentCUDAStream());
+                      v.stride(0), v.stride(1), v.stride(2), (int)which, at::cuda::getCurrentCUDAStream());
+}
+
+// x [b, n, h, d] 16 bit (unit stride on d) -> out, rotated by angles [n, >= d/2] fp32 (sign -1: inverse rotation).
+//   head_major = false: out [b, n, h, d_out] (d_out >= d: the caller pre-zeroes the padding columns)
+//   head_major = true : out [b*h, n, d_out]  (one half of a K/V gather slot)
+void rotary(const Tensor& x, const Tensor& angles, Tensor out, bool head_major, double sign) {
+  check_16bit(x, "x");
+  TORCH_CHECK(x.dim() == 4 && x.stride(3) == 1 && out.is_contiguous() && out.scalar_type() == x.scalar_type());
+  const int b = x.size(0), n = x.size(1), h = x.size(2), d = x.size(3);
+  TORCH_CHECK(d % 16 == 0, "rotary kernel needs head dim % 16 == 0");
+  TORCH_CHECK(angles.is_cuda() && angles.scalar_type() == at::kFloat && angles.dim() == 2 && angles.size(0) == n &&
+              angles.size(1) >= d / 2 && angles.stride(1) == 1);
+  for (int i = 0; i < 3; ++i) TORCH_CHECK(x.stride(i) % 8 == 0, "x strides must be multiples of 8 elements");
+  const int d_out = out.size(-1);
+  TORCH_CHECK(d_out >= d && d_out % 8 == 0 && out.numel() == (int64_t)b * n * h * d_out);
+  long long ob, on, oh;
+  if (head_major) { ob = (long long)h * n * d_out; oh = (long long)n * d_out; on = d_out; }
+  else { ob = (long long)n * h * d_out; on = (long long)h * d_out; oh = d_out; }
+  c10::cuda::CUDAGuard guard(x.device());
+  rab::launch_rotary(x.data_ptr(), out.data_ptr(), angles.data_ptr<float>(), (int)angles.stride(0), b, n, h, d,
+                     x.stride(0), x.stride(1), x.stride(2), ob, on, oh, (float)sign,
+                     x.scalar_type() == at::kBFloat16, at::cuda::getCurrentCUDAStream());
 }
 
 void device_barrier(at::IntArrayRef pad_ptrs, int64_t rank, int64_t epoch) {
@@ -579,12 +622,13 @@ TORCH_LIBRARY(rab, m) {
   m.def("attn_fwd(Tensor q, Tensor kv_buf, int[] peer_ptrs, Tensor ready, Tensor? kmask_bits, int kv_heads, int rank, "
         "bool causal, int window, float scale, float softclamp, int pos_stride, int seg_len, int[] base0, int[] "
         "base1, int q_pos_offset, int[] hop_owner) -> (Tensor, Tensor)");
-  m.def("pack_kv(Tensor k, Tensor v, Tensor(a!) slot) -> ()");
+  m.def("pack_kv(Tensor k, Tensor v, Tensor(a!) slot, int which=3) -> ()");
+  m.def("rotary(Tensor x, Tensor angles, Tensor(a!) out, bool head_major, float sign) -> ()");
   m.def("tree_decode(Tensor q, Tensor? k, Tensor? v, Tensor? k_scale, Tensor? v_scale, Tensor(a!) scratch, Tensor(b!) "
         "group_done, Tensor(c!) counters, int[] partial_ptrs, int aux_local_ptr, int[] pad_ptrs, int mc_partial_ptr, int "
         "mc_aux_ptr, int rank, Tensor(d!) out, int kv_heads, int splits, float scale, int scale_block_keys, float eps, "
-        "int grid) -> ()");
-  m.def("tree_decode_max_ctas(int d, int kv_kind) -> int");
+        "int grid, bool tensor_core) -> ()");
+  m.def("tree_decode_max_ctas(int d, int kv_kind, bool tensor_core) -> int");
   m.def("bwd_prep(Tensor q, Tensor o, Tensor dout, Tensor lse, Tensor(a!) qdo_buf, Tensor(b!) stat_buf, int rank) -> ()");
   m.def("attn_bwd_dq(Tensor qdo_buf, Tensor kv_buf, Tensor stat_buf, Tensor? ready, int ready_target, Tensor? "
         "kmask_bits, int batch, int heads, int kv_heads, int rank, bool causal, int window, float scale, float "
@@ -611,6 +655,7 @@ TORCH_LIBRARY_IMPL(rab, CUDA, m) {
   m.impl("umma_probe", &umma_probe);
   m.impl("attn_fwd", &attn_fwd);
   m.impl("pack_kv", &pack_kv);
+  m.impl("rotary", &rotary);
   m.impl("tree_decode", &tree_decode);
   m.impl("bwd_prep", &bwd_prep);
   m.impl("attn_bwd_dq", &attn_bwd_dq);

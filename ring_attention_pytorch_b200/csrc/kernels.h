@@ -187,14 +187,24 @@ struct TreeDecodeParams {
 };
 int tree_decode_max_ctas(int d, int kv_kind, int num_sms);
 void launch_tree_decode(const TreeDecodeParams& p, int d, int grid, cudaStream_t stream);
+// tcgen05 variant (tree_decode_tc_sm100.cu): head dim 128; map_k / map_v: K, V as (d, n, b*hk) with a 128-byte x 128-key box
+int tree_decode_tc_max_ctas(int kv_kind, int num_sms);
+void launch_tree_decode_tc(const CUtensorMap& map_k, const CUtensorMap& map_v, const TreeDecodeParams& p, int grid,
+                           cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // misc kernels (elementwise_sm100.cu)
 // ------------------------------------------------------------------------------------------------
 // k, v [b, n, hk, d] (arbitrary batch/seq/head strides, unit d stride) -> slot [2][b*hk][n][d]
+// which: bit 0 = pack the K half, bit 1 = pack the V half
 void launch_pack_kv(const void* k, const void* v, void* slot, int batch, int n, int kv_heads, int d,
                     long long k_sb, long long k_sn, long long k_sh, long long v_sb, long long v_sn,
-                    long long v_sh, cudaStream_t stream);
+                    long long v_sh, int which, cudaStream_t stream);
+
+// rotary embedding (rotate-half convention) fused with a layout change; see elementwise_sm100.cu:rotary_kernel
+void launch_rotary(const void* x, void* out, const float* angles, int astride, int batch, int n, int heads, int d,
+                   long long sb, long long sn, long long sh, long long ob, long long on, long long oh, float sign,
+                   int is_bf16, cudaStream_t stream);
 
 // cross-device barrier on symmetric signal pads: every rank bumps its epoch slot on every peer and
 // waits until all peers have bumped its own pad.

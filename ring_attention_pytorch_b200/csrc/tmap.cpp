@@ -55,6 +55,16 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
   return make_tmap_typed(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle);
 }
 
+CUtensorMap make_tmap_u8(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, TmapSwizzle swizzle) {
+  return make_tmap_typed(CU_TENSOR_MAP_DATA_TYPE_UINT8, base, rank, dims, strides_bytes, box, swizzle);
+}
+
+CUtensorMap make_tmap_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box, TmapSwizzle swizzle) {
+  return make_tmap_typed(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rank, dims, strides_bytes, box, swizzle);
+}
+
 CUtensorMap make_tmap_f32(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                           const uint32_t* box, TmapSwizzle swizzle) {
   return make_tmap_typed(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle);

@@ -21,6 +21,12 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
 CUtensorMap make_tmap_f32(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                           const uint32_t* box, TmapSwizzle swizzle);
 
+// same for 8-bit elements (fp8 KV cache tiles consumed by kind::f8f6f4 MMAs)
+CUtensorMap make_tmap_u8(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, TmapSwizzle swizzle);
+CUtensorMap make_tmap_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box, TmapSwizzle swizzle);
+
 inline void cuda_check(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {
     throw std::runtime_error(std::string("[ring_attention_b200] ") + what + ": " + cudaGetErrorString(e));

@@ -323,18 +323,23 @@ class RingAttention(Module):
         if not exists(rotary_emb) and exists(self.rotary_embed):
             rotary_emb = self.rotary_embed(n, ring_size if use_ring else 1) if use_ring else \
                 self.rotary_embed(torch.arange(n, device=x.device))
-        if exists(rotary_emb):
+        any_cuda_inputs = any(t.is_cuda for t in (q, k, v))
+        kernel_path = any_cuda_inputs and self.use_cuda_kernel and not self.force_regular_attn
+        # On the sm_100a path the rotation of q and k happens inside the op's pack kernels (fp32 sincos from the same
+        # angles, fused with the head-major repack): no eager elementwise passes over q and k.
+        fuse_rotary = kernel_path and exists(rotary_emb) and self.dim_head % 16 == 0
+        if exists(rotary_emb) and not fuse_rotary:
             q = apply_rotary_pos_emb(rotary_emb, q)
             k = apply_rotary_pos_emb(rotary_emb, k)
 
-        any_cuda_inputs = any(t.is_cuda for t in (q, k, v))
         if self.force_regular_attn:
             out = default_attention(q, k, v, mask=mask, causal=self.causal)
-        elif any_cuda_inputs and self.use_cuda_kernel:
+        elif kernel_path:
             from ring_attention_pytorch_b200.ops.ring_cuda import ring_flash_attn_cuda
 
             out = ring_flash_attn_cuda(q, k, v, mask, self.causal, self.bucket_size, use_ring,
-                                       self.striped_ring_attn and use_ring, self.max_lookback_seq_len, ring_size)
+                                       self.striped_ring_attn and use_ring, self.max_lookback_seq_len, ring_size,
+                                       rotary_freqs=rotary_emb if fuse_rotary else None)
         else:
             out = ring_flash_attn(q, k, v, mask, self.causal, self.bucket_size, use_ring,
                                   self.striped_ring_attn and use_ring, self.max_lookback_seq_len, ring_size)

@@ -84,6 +84,15 @@ def _ring_gather_workspace(ws, ring_size, b, hk, n_k, d_pad, dt):
     return gather, own_slot_ptrs, slot_bytes
 
 
+def _pack_slot(ops, k: Tensor, v: Tensor, slot: Tensor, angles: Optional[Tensor]) -> None:
+    """K, V [b, n, hk, d] -> head-major slot [2, b*hk, n, d]; with ``angles`` K is rotated on the way in."""
+    if angles is None:
+        ops.pack_kv(k, v, slot, 3)
+    else:
+        ops.rotary(k, angles, slot[0], True, 1.0)
+        ops.pack_kv(k, v, slot, 2)  # V half only
+
+
 class RingFlashAttentionCUDAFunction(Function):
     @staticmethod
     def forward(
@@ -101,6 +110,7 @@ class RingFlashAttentionCUDAFunction(Function):
         softclamp_qk_sim: bool = False,
         softclamp_value: float = 50.0,
         layout: Optional[str] = None,
+        rotary_freqs: Optional[Tensor] = None,
     ):
         assert q.is_cuda and k.is_cuda and v.is_cuda, "ring_flash_attn_cuda needs CUDA tensors"
         ops = _ext.ops()
@@ -126,7 +136,28 @@ class RingFlashAttentionCUDAFunction(Function):
         assert d <= 128, "head dimension up to 128 is supported"
         d_pad = 64 if d <= 64 else 128
         scale = d ** -0.5
-        qp, kp, vp = (_pad_head_dim(t, d_pad).contiguous() for t in (q, k, v))
+        # Rotary embedding (rotate-half pairs, reference ring_attention.py:160-172) is applied by the op's own pack
+        # kernels: Q into its padded contiguous copy, K straight into the gather slot; the backward rotates dQ / dK back.
+        ang = None
+        fused_k_rotary = False
+        if exists(rotary_freqs):
+            assert not cross_attn and d % 16 == 0, "in-kernel rotary needs self-attention and head dim % 16 == 0"
+            ang = rotary_freqs.detach().to(device=q.device, dtype=torch.float32).contiguous()
+            assert ang.dim() == 2 and ang.shape[0] == n_q and ang.shape[1] >= d // 2
+            q_rot = (torch.zeros if d_pad != d else torch.empty)(b, n_q, h, d_pad, dtype=dt, device=q.device)
+            ops.rotary(q, ang, q_rot, False, 1.0)
+            _count()
+            qp = q_rot
+            fused_k_rotary = d_pad == d
+            if not fused_k_rotary:
+                k_rot = torch.empty(b, n_k, hk, d, dtype=dt, device=q.device)
+                ops.rotary(k, ang, k_rot, False, 1.0)
+                _count()
+                kp, vp = (_pad_head_dim(t, d_pad).contiguous() for t in (k_rot, v))
+            else:
+                kp, vp = k, v  # unit stride on d is all the pack kernels need
+        else:
+            qp, kp, vp = (_pad_head_dim(t, d_pad).contiguous() for t in (q, k, v))
 
         rank = get_rank() % ring_size if use_ring else 0
         pm = make_position_map(layout, ring_size, n_k)
@@ -140,7 +171,7 @@ class RingFlashAttentionCUDAFunction(Function):
             if use_ring:
                 ws = get_workspace(ring_size, dev)
                 kv_gather, own_slot_ptrs, _ = _ring_gather_workspace(ws, ring_size, b, hk, n_k, d_pad, dt)
-                ops.pack_kv(kp, vp, kv_gather[rank])
+                _pack_slot(ops, kp, vp, kv_gather[rank], ang if fused_k_rotary else None)
                 ws.barrier()  # every peer's own slot is complete
                 _count(2)
                 peers = [0 if o == rank else own_slot_ptrs[o] for o in range(ring_size)]
@@ -148,7 +179,7 @@ class RingFlashAttentionCUDAFunction(Function):
                     kbits = pack_key_mask_bits(_gather_ring_masks(mask, ring_size))
             else:
                 kv_gather = alloc_kv_buffer(1, b, hk, n_k, d_pad, dt, dev)
-                ops.pack_kv(kp, vp, kv_gather[0])
+                _pack_slot(ops, kp, vp, kv_gather[0], ang if fused_k_rotary else None)
                 _count()
                 if exists(mask):
                     kbits = pack_key_mask_bits(mask[None])
@@ -160,11 +191,12 @@ class RingFlashAttentionCUDAFunction(Function):
         _count()
 
         ctx.cfg = (causal, max_lookback_seq_len, ring_size, rank, layout, softclamp, scale, q_off, use_ring, d, d_pad,
-                   orig_dtype, hk)
+                   orig_dtype, hk, fused_k_rotary)
         # single rank: the packed K/V is exactly what the backward needs; ring: keep the (small) inputs, re-pack later
         none = torch.empty(0, device=dev)
         ctx.save_for_backward(qp, kp if use_ring else none, vp if use_ring else none, o, lse,
-                              none if use_ring else kv_gather, kbits if kbits is not None else none)
+                              none if use_ring else kv_gather, kbits if kbits is not None else none,
+                              ang if ang is not None else none)
         out = o[..., :d]
         return out.to(orig_dtype) if orig_dtype != dt else out
 
@@ -172,9 +204,10 @@ class RingFlashAttentionCUDAFunction(Function):
     def backward(ctx, do: Tensor):
         ops = _ext.ops()
         (causal, window, ring_size, rank, layout, softclamp, scale, q_off, use_ring, d, d_pad, orig_dtype,
-         hk) = ctx.cfg
-        qp, kp, vp, o, lse, kv_saved, kbits = ctx.saved_tensors
+         hk, fused_k_rotary) = ctx.cfg
+        qp, kp, vp, o, lse, kv_saved, kbits, ang = ctx.saved_tensors
         kbits = kbits if kbits.numel() > 0 else None
+        ang = ang if ang.numel() > 0 else None
         dt = qp.dtype
         b, n_q, h, _ = qp.shape
         dev = qp.device
@@ -188,7 +221,7 @@ class RingFlashAttentionCUDAFunction(Function):
         if use_ring:  # rebuild the gather buffer around this rank's own slot (the forward's buffer is long reused)
             ws = get_workspace(ring_size, dev)
             kv_gather, kv_own_ptrs, kv_bytes = _ring_gather_workspace(ws, ring_size, b, hk, n_k, d_pad, dt)
-            ops.pack_kv(kp, vp, kv_gather[rank])
+            _pack_slot(ops, kp, vp, kv_gather[rank], ang if fused_k_rotary else None)
             _count()
         else:
             kv_gather = kv_saved
@@ -286,9 +319,15 @@ class RingFlashAttentionCUDAFunction(Function):
             _count(2)
 
         dq, dk, dv = dq[..., :d], dk[..., :d], dv[..., :d]
+        if ang is not None:  # gradients w.r.t. the un-rotated q / k: rotate back (the rotation is orthogonal)
+            dq_in, dk_in = torch.empty(b, n_q, h, d, dtype=dt, device=dev), torch.empty(b, n_k, hk, d, dtype=dt, device=dev)
+            ops.rotary(dq, ang, dq_in, False, -1.0)
+            ops.rotary(dk, ang, dk_in, False, -1.0)
+            _count(2)
+            dq, dk = dq_in, dk_in
         if orig_dtype != dt:
             dq, dk, dv = dq.to(orig_dtype), dk.to(orig_dtype), dv.to(orig_dtype)
-        return dq, dk, dv, None, None, None, None, None, None, None, None, None, None
+        return dq, dk, dv, None, None, None, None, None, None, None, None, None, None, None
 
 
 ring_flash_attn_cuda_ = RingFlashAttentionCUDAFunction.apply
@@ -309,8 +348,12 @@ def ring_flash_attn_cuda(
     softclamp_qk_sim: bool = False,
     softclamp_value: float = 50.0,
     layout: Optional[str] = None,
+    rotary_freqs: Optional[Tensor] = None,
 ) -> Tensor:
     """q [b, n, h, d]; k, v [b, n, hk, d] (this rank's shard when ``ring_reduce_col``).  ``bucket_size`` is
-    accepted for signature parity; tiling is fixed by the kernel (128 x 128)."""
+    accepted for signature parity; tiling is fixed by the kernel (128 x 128).  ``rotary_freqs`` ([n, d] or [n, d/2]
+    fp32 angles, e.g. the output of ``RingRotaryEmbedding``): rotary embedding of q and k applied inside the op's pack
+    kernels instead of by eager PyTorch passes."""
     return ring_flash_attn_cuda_(q, k, v, mask, causal, bucket_size, ring_reduce_col, striped_ring_attn,
-                                 max_lookback_seq_len, ring_size, softclamp_qk_sim, softclamp_value, layout)
+                                 max_lookback_seq_len, ring_size, softclamp_qk_sim, softclamp_value, layout,
+                                 rotary_freqs)

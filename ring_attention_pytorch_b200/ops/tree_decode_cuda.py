@@ -20,8 +20,10 @@ from ring_attention_pytorch_b200.ops import _ext
 from ring_attention_pytorch_b200.parallel.distributed import get_rank, get_world_size, is_distributed
 
 LAUNCHES = {"count": 0}
-# "auto": use the NVSwitch multicast mapping when torch's symmetric memory can provide one, else NVLink peer loads
-CONFIG = {"nvls": "auto"}
+# nvls "auto": use the NVSwitch multicast mapping when torch's symmetric memory can provide one, else NVLink peer loads
+# tensor_core "auto": head dim 128 shards of at least one 128-key tile run the tcgen05 kernel (K / V tiles go from TMA
+#                     straight into the MMA; fp8 caches use kind::f8f6f4), everything else the CUDA-core kernel
+CONFIG = {"nvls": "auto", "tensor_core": "auto"}
 K_MAX_WORLD = 16
 PAD_WORDS = 2 * K_MAX_WORLD  # two signal rounds
 
@@ -159,16 +161,18 @@ def tree_decode_cuda(
     else:
         k = v = None
     g = h // hk
-    groups = b * hk * ((g + 3) // 4)
     kv_kind = 0 if k is None or k.dtype == torch.bfloat16 else (1 if k.dtype == torch.float16 else 2)
-    resident = int(ops.tree_decode_max_ctas(d, kv_kind))
+    tc = CONFIG["tensor_core"]
+    use_tc = tc in ("auto", True, "on") and d == 128 and n >= 128
+    groups = b * hk * ((g + 15) // 16 if use_tc else (g + 3) // 4)
+    resident = int(ops.tree_decode_max_ctas(d, kv_kind, use_tc))
     splits = _choose_splits(n, groups, resident)
     buf = _buffers(b * h, d, dev)
     need = b * hk * splits * g * (d + 4)
     if buf.scratch is None or buf.scratch.numel() < need:
         buf.scratch = torch.empty(need, dtype=torch.float32, device=dev)
-    if buf.group_done is None or buf.group_done.numel() < groups:
-        buf.group_done = torch.zeros(groups, dtype=torch.int32, device=dev)
+    if buf.group_done is None or buf.group_done.numel() < b * hk * ((g + 3) // 4):
+        buf.group_done = torch.zeros(b * hk * ((g + 3) // 4), dtype=torch.int32, device=dev)
     if out is None:
         out_dtype = q.dtype if q.dtype in (torch.bfloat16, torch.float16) else torch.float32
         out = torch.empty(b, h, 1, d, dtype=out_dtype, device=dev)
@@ -176,6 +180,6 @@ def tree_decode_cuda(
     grid = max(1, min(resident, max(units, (b * h + 3) // 4)))
     ops.tree_decode(q3, k, v, k_scale, v_scale, buf.scratch, buf.group_done, buf.counters, buf.partial_ptrs,
                     buf.aux_local_ptr, buf.pad_ptrs, buf.mc_partial_ptr, buf.mc_aux_ptr, buf.rank, out.view(b, h, d), hk,
-                    splits, d ** -0.5, scale_block_keys, eps, grid)
+                    splits, d ** -0.5, scale_block_keys, eps, grid, use_tc)
     LAUNCHES["count"] += 1
     return out

@@ -78,6 +78,17 @@ def zig_zag_attn(
     if causal is None:
         causal = attn_mask is None and False
 
+    if attn_mask is None and causal and dropout > 0.0:
+        # The fused ring kernels have no dropout.  Honour the argument like the reference does (it forwards dropout to
+        # SDPA, zig_zag_attention.py:134-138) by taking the gathered dense path with the causal mask of the zig-zag
+        # positions instead of silently ignoring it.
+        world = get_world_size() if is_distributed() else 1
+        rank = get_rank() if is_distributed() else 0
+        pm = make_position_map("zigzag" if world > 1 else "plain", world, q.shape[-2])
+        q_pos = pm.positions(rank, q.device)
+        k_pos = torch.cat([pm.positions(r, q.device) for r in range(world)])
+        attn_mask = q_pos[:, None] >= k_pos[None, :]
+
     if attn_mask is None and causal:
         # ring schedule with the zig-zag position map: no all-gather, no dense mask
         qn, kn, vn = (t.transpose(1, 2) for t in (q, k, v))

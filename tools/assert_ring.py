@@ -6,6 +6,7 @@
     python tools/assert_ring.py attn --world-size 4 --num-sharded-batches 2 --causal
     python tools/assert_ring.py flash --causal --rand-key-pad-mask --softclamp-qk-sim
     python tools/assert_ring.py tree --world-size 8 --seq-len 5
+    python tools/assert_ring.py zigzag --world-size 4 --seq-len 61
     python tools/assert_ring.py transformer --world-size 2 --use-cuda --causal --striped-ring-attn   # on a GPU box
 
 Unlike the reference drivers the oracle is the dense fp32 model, gradients are compared with random-cotangent
@@ -117,8 +118,47 @@ def _tree_worker(rank, world, port, o):
     dist.destroy_process_group()
 
 
+def _zigzag_worker(rank, world, port, o):
+    """Counterpart of the reference's assert_zig_zag.py:99-131: a causal attention layer evaluated on zig-zag shards
+    (pad -> shard -> attn -> inverse) against the same layer on the full sequence, outputs and input gradients."""
+    from ring_attention_pytorch_b200 import default_attention, zig_zag_attn, zig_zag_pad_seq, zig_zag_shard
+
+    _setup(rank, world, port, o["use_cuda"])
+    dev = torch.device("cuda", rank) if o["use_cuda"] else torch.device("cpu")
+    dt = torch.bfloat16 if o["use_cuda"] else torch.float32
+    torch.manual_seed(0)
+    b, h, hk, d, n = o["batch_size"], o["heads"], max(1, o["heads"] // o["num_grouped_query_heads"]), o["dim_head"], o["seq_len"]
+    q = torch.randn(b, h, n, d, device=dev, dtype=dt)
+    k = torch.randn(b, hk, n, d, device=dev, dtype=dt)
+    v = torch.randn(b, hk, n, d, device=dev, dtype=dt)
+    g = torch.randn(b, h, n, d, device=dev, dtype=dt)
+    qf, kf, vf = (t.detach().float().clone().requires_grad_() for t in (q, k, v))
+    ref = default_attention(qf.transpose(1, 2), kf.transpose(1, 2), vf.transpose(1, 2), causal=True).transpose(1, 2)
+    (ref * g.float()).sum().backward()
+
+    qz, kz, vz = (t.detach().clone().requires_grad_() for t in (q, k, v))
+    padded = [zig_zag_pad_seq(t)[0] for t in (qz, kz, vz)]
+    (ql, _, _), inverse = zig_zag_shard(padded[0])
+    (kl, _, _), _ = zig_zag_shard(padded[1])
+    (vl, _, _), _ = zig_zag_shard(padded[2])
+    out = inverse(zig_zag_attn(ql, kl, vl, causal=True))[..., :n, :]
+    (out.float() * g.float()).sum().backward()
+    tol = 5e-2 if o["use_cuda"] else 1e-4
+    _check("zig-zag output", out, ref, tol)
+    # Every rank evaluates the same replicated loss on the re-assembled output, so the all-gather's backward hands each
+    # shard the sum over ranks (world x the true gradient), and a rank only touches its own two chunks of its input
+    # copy: the full gradient is the sum over ranks divided by the world size.
+    for t in (qz, kz, vz):
+        dist.all_reduce(t.grad)
+        t.grad /= world
+    _check("zig-zag dq", qz.grad, qf.grad, tol * max(1.0, qf.grad.abs().max().item()))
+    _check("zig-zag dk", kz.grad, kf.grad, tol * max(1.0, kf.grad.abs().max().item()))
+    _check("zig-zag dv", vz.grad, vf.grad, tol * max(1.0, vf.grad.abs().max().item()))
+    dist.destroy_process_group()
+
+
 @click.command()
-@click.argument("what", type=click.Choice(["transformer", "attn", "flash", "tree"]))
+@click.argument("what", type=click.Choice(["transformer", "attn", "flash", "tree", "zigzag"]))
 @click.option("--world-size", default=2)
 @click.option("--batch-size", default=2)
 @click.option("--num-sharded-batches", default=1)
@@ -159,6 +199,8 @@ def main(what, **o):
     port = _free_port()
     if what == "tree":
         mp.spawn(_tree_worker, args=(o["world_size"], port, o), nprocs=o["world_size"], join=True)
+    elif what == "zigzag":
+        mp.spawn(_zigzag_worker, args=(o["world_size"], port, o), nprocs=o["world_size"], join=True)
     else:
         mp.spawn(_model_worker, args=(o["world_size"], port, what, o), nprocs=o["world_size"], join=True)
 

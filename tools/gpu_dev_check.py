@@ -326,9 +326,12 @@ def case_perf_bwd(n=16384, h=16, d=128, causal=True, iters=5, b=1, hk=None):
     return res
 
 
-def case_perf_decode(batch=256, h=32, hk=8, n=8192, d=128, fp8=False, iters=20):
+def case_perf_decode(batch=256, h=32, hk=8, n=8192, d=128, fp8=False, iters=20, tensor_core="auto"):
     import torch
+    from ring_attention_pytorch_b200.ops import tree_decode_cuda as tdc
     from ring_attention_pytorch_b200.ops.tree_decode_cuda import tree_decode_cuda
+
+    tdc.CONFIG["tensor_core"] = tensor_core
 
     q = torch.randn(batch, h, 1, d, device="cuda", dtype=torch.bfloat16)
     k = torch.randn(batch, hk, n, d, device="cuda", dtype=torch.bfloat16)
@@ -356,7 +359,7 @@ def case_perf_decode(batch=256, h=32, hk=8, n=8192, d=128, fp8=False, iters=20):
     ref = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), vx)
     err = (out[:2].float() - ref).abs().max().item()
     return {"ms": ms, "kv_gb_per_s": kv_bytes / ms / 1e6, "hbm_frac_of_6585": kv_bytes / ms / 1e6 / 6585.0, "err": err,
-            "ok": err < 3e-2}
+            "tensor_core": tensor_core, "launches_per_step": 1, "ok": err < 3e-2}
 
 
 def case_perf(n=16384, h=16, d=128, causal=True, iters=5, b=1, hk=None):
@@ -487,6 +490,9 @@ CASES = {
     "perfdec_bf16": lambda: case_perf_decode(),
     "perfdec_fp8": lambda: case_perf_decode(fp8=True),
     "perfdec_mha_b32": lambda: case_perf_decode(batch=32, h=32, hk=32, n=8192),
+    "perfdec_cudacore_bf16": lambda: case_perf_decode(tensor_core=False),
+    "perfdec_cudacore_fp8": lambda: case_perf_decode(fp8=True, tensor_core=False),
+    "perfdec_g16_bf16": lambda: case_perf_decode(batch=64, h=64, hk=4, n=16384),
     "perf_causal_16k": lambda: case_perf(),
     "perf_full_8k": lambda: case_perf(n=8192, causal=False),
     "perf_causal_64k_h8": lambda: case_perf(n=65536, h=8, iters=3),
