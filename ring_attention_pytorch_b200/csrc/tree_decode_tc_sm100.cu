@@ -300,11 +300,20 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
       // P must stay below the e4m3 maximum (448) and its small values above the subnormals (2^-9): slack 4, scale 2^4.
       constexpr float RAISE_SLACK = KV8 ? 4.f : 8.f;
       constexpr float P_SCALE = KV8 ? 16.f : 1.f;
+      // V block scales ride on the probabilities RELATIVE to the largest scale of the unit (so an fp8 P never underflows
+      // because of a small dequantisation scale); the reference scale itself is applied once in the epilogue.
+      float vs_ref = 1.f;
+      if (vsb != nullptr && ntiles > 0) {
+        vs_ref = 0.f;
+        for (int blk = k0 / p.scale_block; blk <= (k1 - 1) / p.scale_block; ++blk) vs_ref = fmaxf(vs_ref, vsb[blk]);
+        if (!(vs_ref > 0.f)) vs_ref = 1.f;
+      }
+      const float inv_vs_ref = 1.f / vs_ref;
       for (int t = 0; t < ntiles; ++t) {
         const uint32_t n = n_tile + t, sb = n & 1, pb = n & 1;
         const int key0 = k0 + t * TC_TILE;
         const float ks = ksb ? ksb[key0 / p.scale_block] : 1.f;
-        const float vs = vsb ? vsb[key0 / p.scale_block] : 1.f;
+        const float vs = vsb ? vsb[key0 / p.scale_block] * inv_vs_ref : 1.f;
         mbar_wait(&sm.s_full[sb], (n >> 1) & 1, 2200 + sb);
         tc_fence_after();
         uint32_t sr[16];
@@ -414,7 +423,7 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
           if (h < g) {
             const int head = (g0 + h) * p.kv_heads + kvh;
             float* row = my_partial + ((size_t)b * p.heads + head) * row_stride;
-            const float inv = l_tot[h] > 0.f ? 1.f / (l_tot[h] * P_SCALE) : 0.f;
+            const float inv = l_tot[h] > 0.f ? vs_ref / (l_tot[h] * P_SCALE) : 0.f;
             row[r] = __uint_as_float(orr[h]) * inv;
             if (r == 0) {
               row[D] = l_tot[h] > 0.f ? m_run[h] + log2f(l_tot[h]) : -INFINITY;
@@ -427,7 +436,7 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
 #pragma unroll
         for (int h = 0; h < TC_NH; ++h) {
           if (h < g) {
-            out[h * row_stride + r] = __uint_as_float(orr[h]) * (1.f / P_SCALE);
+            out[h * row_stride + r] = __uint_as_float(orr[h]) * (vs_ref / P_SCALE);
             if (r == 0) {
               out[h * row_stride + D] = m_run[h];
               out[h * row_stride + D + 1] = l_tot[h];

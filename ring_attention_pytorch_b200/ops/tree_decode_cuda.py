@@ -163,7 +163,8 @@ def tree_decode_cuda(
     g = h // hk
     kv_kind = 0 if k is None or k.dtype == torch.bfloat16 else (1 if k.dtype == torch.float16 else 2)
     tc = CONFIG["tensor_core"]
-    use_tc = tc in ("auto", True, "on") and d == 128 and n >= 128
+    # a 128-key tile of the tensor-core kernel must lie inside one scale block
+    use_tc = tc in ("auto", True, "on") and d == 128 and n >= 128 and scale_block_keys % 128 == 0
     groups = b * hk * ((g + 15) // 16 if use_tc else (g + 3) // 4)
     resident = int(ops.tree_decode_max_ctas(d, kv_kind, use_tc))
     splits = _choose_splits(n, groups, resident)

@@ -211,3 +211,40 @@ def test_poly_exp2_reference():
     assert np.max(np.abs(got - ref) / ref) < 1.5e-4
     special = poly_exp2(np.array([-np.inf, -1000.0, 0.0], dtype=np.float32))
     assert special[0] == 0.0 and special[1] == 0.0 and special[2] == 1.0
+
+
+def test_transformer_loss_ignores_padded_targets():
+    """Derived labels are x[:, 1:], so their validity is mask[:, 1:] (reference ring_attention.py:614): the first pad token of
+    a right-padded sequence must not be trained as a target."""
+    import torch.nn.functional as F
+
+    from ring_attention_pytorch_b200 import RingTransformer
+
+    torch.manual_seed(0)
+    model = RingTransformer(num_tokens=64, dim=32, depth=1, causal=True, dim_head=8, heads=4, bucket_size=8, ring_attn=False,
+                            use_cuda_kernel=False)
+    x = torch.randint(0, 64, (3, 17))
+    lengths = torch.tensor([17, 9, 4])
+    mask = torch.arange(17)[None, :] < lengths[:, None]
+    loss = model(x, mask=mask, return_loss=True)
+    logits = model(x[:, :-1], mask=mask[:, :-1])
+    labels = x[:, 1:].masked_fill(~mask[:, 1:], model.ignore_index)
+    want = F.cross_entropy(logits.transpose(1, 2), labels, ignore_index=model.ignore_index)
+    assert torch.allclose(loss, want, atol=1e-6), (loss, want)
+    # the shifted-by-one mask (what round 1 used) gives a different number on this batch
+    wrong = F.cross_entropy(logits.transpose(1, 2), x[:, 1:].masked_fill(~mask[:, :-1], model.ignore_index),
+                            ignore_index=model.ignore_index)
+    assert not torch.allclose(want, wrong, atol=1e-4)
+
+
+def test_argument_validation_names_the_offending_argument():
+    from ring_attention_pytorch_b200.utils.validate import check_attention_inputs
+
+    q = torch.randn(2, 8, 4, 16)
+    k = torch.randn(2, 8, 3, 16)
+    with pytest.raises(ValueError, match="multiple of key/value heads"):
+        check_attention_inputs(q, k, k)
+    k = torch.randn(2, 8, 2, 16)
+    with pytest.raises(ValueError, match="mask must be bool"):
+        check_attention_inputs(q, k, k, torch.ones(2, 7, dtype=torch.bool))
+    check_attention_inputs(q, k, k, torch.ones(2, 8, dtype=torch.bool))

@@ -94,15 +94,19 @@ def bench_decode(world, rank, dev, n_per_rank, batch, iters):
     ):
         ms = timed(lambda: tree_decode_cuda(q, kk, vv, dim_v=d, k_scale=ks, v_scale=vs), world, warmup=5, iters=iters)
         kv_bytes = 2 * kk.numel() * kk.element_size()
+        from ring_attention_pytorch_b200.ops import tree_decode_cuda as tdc
+
         emit(rank, bench="tree_decode", kv_dtype=name, n_gpus=world, keys_per_rank=n_per_rank, batch=batch, ms=ms,
-             local_kv_gb_per_s=kv_bytes / ms / 1e6, tokens_per_s=batch / (ms * 1e-3))
+             local_kv_gb_per_s=kv_bytes / ms / 1e6, hbm_frac_of_measured_6585=kv_bytes / ms / 1e6 / 6585.0,
+             tokens_per_s=batch / (ms * 1e-3), launches_per_step=1, merge="nvls multimem" if tdc.uses_nvls(q) else "nvlink peer loads",
+             nvls_unavailable_because=tdc._alloc_symmetric.last_error)
 
 
-def bench_sweep(world, rank, dev, iters):
+def bench_sweep(world, rank, dev, iters, sizes=(4096, 16384, 65536, 262144, 1048576)):
     from ring_attention_pytorch_b200.ops.ring_cuda import ring_flash_attn_cuda
 
     h, d = 32, 128
-    for total in (4096, 16384, 65536, 262144, 1048576):
+    for total in sizes:
         n = total // world
         if n < 128:
             continue
@@ -138,6 +142,7 @@ def main():
     ap.add_argument("--keys-per-rank", type=int, default=8192)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--sweep-sizes", default="4096,16384,65536,262144,1048576")
     args = ap.parse_args()
     world, rank, dev = setup()
     for which in args.which.split(","):
@@ -146,7 +151,7 @@ def main():
         elif which == "decode":
             bench_decode(world, rank, dev, args.keys_per_rank, args.batch, max(args.iters, 10))
         elif which == "sweep":
-            bench_sweep(world, rank, dev, args.iters)
+            bench_sweep(world, rank, dev, args.iters, tuple(int(x) for x in args.sweep_sizes.split(",")))
     if world > 1:
         dist.destroy_process_group()
 

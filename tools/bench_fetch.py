@@ -90,9 +90,9 @@ def main():
     for it in range(args.iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for o in range(world):
-            if o != rank:
-                ops.peer_copy(gather[o], own_ptrs[o], slot_bytes)
+        for s_ in range(1, world):  # staggered like the backward's pull (r-1, r-2, ...): no two ranks hit one source at once
+            o = (rank - s_) % world
+            ops.peer_copy(gather[o], own_ptrs[o], slot_bytes)
         e1.record()
         torch.cuda.synchronize()
         ce.append(pulled / (e0.elapsed_time(e1) * 1e6))
