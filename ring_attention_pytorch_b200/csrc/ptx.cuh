@@ -295,6 +295,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
 // registers -> TMEM, shape 32x32b.
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
   asm volatile(

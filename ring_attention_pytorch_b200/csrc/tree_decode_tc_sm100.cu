@@ -86,7 +86,21 @@ __device__ __forceinline__ bool wg_vote_any(bool pred) {
 }
 __device__ __forceinline__ void wg_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
-template <bool KV8, int Q16 /* 0: bf16 cache, 1: fp16 cache (ignored for fp8) */>
+// GM: compile-time bound on the query heads of a unit (4 or 16).  The MMA always has N = 16 columns, but the softmax
+// warpgroup runs ONE warp per sub-partition, so every instruction of its per-tile loop is exposed latency: with the
+// usual group sizes (<= 4) the loops, the TMEM loads and the P stores are a quarter of the 16-wide version.
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
+  if constexpr (N == 4) tmem_ld4(taddr, r);
+  else tmem_ld16(taddr, r);
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* r) {
+  if constexpr (N == 4) tmem_st4(taddr, r);
+  else tmem_st16(taddr, r);
+}
+
+template <bool KV8, int Q16 /* 0: bf16 cache, 1: fp16 cache (ignored for fp8) */, int GM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                       const __grid_constant__ TreeDecodeParams p) {
@@ -102,7 +116,7 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int g_total = p.heads / p.kv_heads;
-  const int zchunks = (g_total + TC_NH - 1) / TC_NH;
+  const int zchunks = (g_total + GM - 1) / GM;
   const int groups = p.batch * p.kv_heads * zchunks;
   const int total_units = p.n > 0 ? groups * p.splits : 0;
   constexpr int row_stride = TdCall<D>::row_stride;
@@ -157,8 +171,8 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
     const int zc = grp % zchunks;
     const int bhk = grp / zchunks;
     const int b = bhk / p.kv_heads, kvh = bhk % p.kv_heads;
-    const int g0 = zc * TC_NH;
-    const int g = min(TC_NH, g_total - g0);
+    const int g0 = zc * GM;
+    const int g = min(GM, g_total - g0);
     const int per = ((p.n + p.splits - 1) / p.splits + TC_TILE - 1) / TC_TILE * TC_TILE;
     const int k0 = split * per, k1 = min(p.n, k0 + per);
     const int ntiles = k1 > k0 ? (k1 - k0 + TC_TILE - 1) / TC_TILE : 0;
@@ -288,9 +302,9 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
       const uint32_t lane_off = uint32_t((warp % 4) * 32) << 16;  // TMEM lane quadrant of this warp
       const int r = (warp % 4) * 32 + lane;                      // TMEM lane == key row == d index (epilogue)
       (void)wt;
-      float m_run[TC_NH], l_part[TC_NH];
+      float m_run[GM], l_part[GM];
 #pragma unroll
-      for (int h = 0; h < TC_NH; ++h) {
+      for (int h = 0; h < GM; ++h) {
         m_run[h] = -INFINITY;
         l_part[h] = 0.f;
       }
@@ -316,16 +330,16 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
         const float vs = vsb ? vsb[key0 / p.scale_block] * inv_vs_ref : 1.f;
         mbar_wait(&sm.s_full[sb], (n >> 1) & 1, 2200 + sb);
         tc_fence_after();
-        uint32_t sr[16];
-        tmem_ld16(s_tm[sb] + lane_off, sr);
+        uint32_t sr[GM];
+        tmem_ld_n<GM>(s_tm[sb] + lane_off, sr);
         tc_wait_ld();
         tc_fence_before();
         mbar_arrive(&sm.s_free[sb]);
         const bool live = key0 + r < k1;
-        float sv[TC_NH];
+        float sv[GM];
         bool raise = false;
 #pragma unroll
-        for (int h = 0; h < TC_NH; ++h) {
+        for (int h = 0; h < GM; ++h) {
           float x = __uint_as_float(sr[h]) * ks;
           if constexpr (KV8) x *= sm.qscale[h];
           sv[h] = (live && h < g) ? x : -INFINITY;
@@ -334,16 +348,16 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
         if (wg_vote_any(raise)) {
           // rare: raise the running maxima (all 128 threads agree on them), rescale l and the O^T accumulator
 #pragma unroll
-          for (int h = 0; h < TC_NH; ++h) {
+          for (int h = 0; h < GM; ++h) {
             float mx = sv[h];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if (lane == 0) sm.red[warp % 4][h] = mx;
           }
           wg_sync();
-          float f[TC_NH];
+          float f[GM];
 #pragma unroll
-          for (int h = 0; h < TC_NH; ++h) {
+          for (int h = 0; h < GM; ++h) {
             const float mx = fmaxf(fmaxf(sm.red[0][h], sm.red[1][h]), fmaxf(sm.red[2][h], sm.red[3][h]));
             const float m_new = fmaxf(m_run[h], mx);
             f[h] = (m_run[h] == -INFINITY) ? 0.f : fast_exp2(m_run[h] - m_new);
@@ -356,12 +370,12 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
             const uint32_t np = n - 1;
             mbar_wait(&sm.p_free[np & 1], (np >> 1) & 1, 2210);
             tc_fence_after();
-            uint32_t orr[16];
-            tmem_ld16(o_tm + lane_off, orr);
+            uint32_t orr[GM];
+            tmem_ld_n<GM>(o_tm + lane_off, orr);
             tc_wait_ld();
 #pragma unroll
-            for (int h = 0; h < TC_NH; ++h) orr[h] = __float_as_uint(__uint_as_float(orr[h]) * f[h]);
-            tmem_st16(o_tm + lane_off, orr);
+            for (int h = 0; h < GM; ++h) orr[h] = __float_as_uint(__uint_as_float(orr[h]) * f[h]);
+            tmem_st_n<GM>(o_tm + lane_off, orr);
             tc_wait_st();
             tc_fence_before();
           }
@@ -371,7 +385,7 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
         if (n >= 2) mbar_wait(&sm.p_free[pb], ((n >> 1) - 1) & 1, 2220 + pb);
         uint8_t* pt = sm.p[pb];
 #pragma unroll
-        for (int h = 0; h < TC_NH; ++h) {
+        for (int h = 0; h < GM; ++h) {
           if (h < g) {
             const float pj = sv[h] == -INFINITY ? 0.f : fast_exp2(sv[h] - m_run[h]);
             l_part[h] += pj;
@@ -396,30 +410,30 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
       // ---- epilogue: O^T (lane = d) / l -> partial rows, or the split scratch -------------------------------------------
       // row sums: every thread holds the sum over ITS keys; reduce over the 128 threads
 #pragma unroll
-      for (int h = 0; h < TC_NH; ++h) {
+      for (int h = 0; h < GM; ++h) {
         float sum = l_part[h];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (lane == 0) sm.red[warp % 4][h] = sum;
       }
       wg_sync();
-      float l_tot[TC_NH];
+      float l_tot[GM];
 #pragma unroll
-      for (int h = 0; h < TC_NH; ++h) l_tot[h] = (sm.red[0][h] + sm.red[1][h]) + (sm.red[2][h] + sm.red[3][h]);
-      uint32_t orr[16];
+      for (int h = 0; h < GM; ++h) l_tot[h] = (sm.red[0][h] + sm.red[1][h]) + (sm.red[2][h] + sm.red[3][h]);
+      uint32_t orr[GM];
       if (ntiles > 0) {
         mbar_wait(&sm.o_done, n_unit & 1, 2230);
         tc_fence_after();
-        tmem_ld16(o_tm + lane_off, orr);
+        tmem_ld_n<GM>(o_tm + lane_off, orr);
         tc_wait_ld();
         tc_fence_before();
       } else {
 #pragma unroll
-        for (int h = 0; h < 16; ++h) orr[h] = 0u;
+        for (int h = 0; h < GM; ++h) orr[h] = 0u;
       }
       if (p.splits == 1) {
 #pragma unroll
-        for (int h = 0; h < TC_NH; ++h) {
+        for (int h = 0; h < GM; ++h) {
           if (h < g) {
             const int head = (g0 + h) * p.kv_heads + kvh;
             float* row = my_partial + ((size_t)b * p.heads + head) * row_stride;
@@ -434,7 +448,7 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
       } else {
         float* out = p.scratch + (((size_t)bhk * p.splits + split) * g_total + g0) * row_stride;
 #pragma unroll
-        for (int h = 0; h < TC_NH; ++h) {
+        for (int h = 0; h < GM; ++h) {
           if (h < g) {
             out[h * row_stride + r] = __uint_as_float(orr[h]) * (vs_ref / P_SCALE);
             if (r == 0) {
@@ -502,19 +516,19 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
 }
 
 template <bool KV8, int Q16>
-const void* tc_kernel_ptr() {
-  return (const void*)tree_decode_tc_kernel<KV8, Q16>;
+const void* tc_kernel_ptr(bool small_group) {
+  return small_group ? (const void*)tree_decode_tc_kernel<KV8, Q16, 4> : (const void*)tree_decode_tc_kernel<KV8, Q16, 16>;
 }
-const void* pick_tc(int kv_kind) {
-  if (kv_kind == 2) return tc_kernel_ptr<true, 0>();
-  return kv_kind == 0 ? tc_kernel_ptr<false, 0>() : tc_kernel_ptr<false, 1>();
+const void* pick_tc(int kv_kind, bool small_group) {
+  if (kv_kind == 2) return tc_kernel_ptr<true, 0>(small_group);
+  return kv_kind == 0 ? tc_kernel_ptr<false, 0>(small_group) : tc_kernel_ptr<false, 1>(small_group);
 }
 size_t tc_smem(int kv_kind) { return (kv_kind == 2 ? sizeof(TcSmem<true>) : sizeof(TcSmem<false>)) + 1024; }
 
 }  // namespace
 
 int tree_decode_tc_max_ctas(int kv_kind, int num_sms) {
-  const void* fn = pick_tc(kv_kind);
+  const void* fn = pick_tc(kv_kind, false);
   const size_t smem = tc_smem(kv_kind);
   cuda_check(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "tree_decode_tc smem attr");
   int per_sm = 0;
@@ -524,7 +538,7 @@ int tree_decode_tc_max_ctas(int kv_kind, int num_sms) {
 
 void launch_tree_decode_tc(const CUtensorMap& map_k, const CUtensorMap& map_v, const TreeDecodeParams& p, int grid,
                            cudaStream_t stream) {
-  const void* fn = pick_tc(p.kv_kind);
+  const void* fn = pick_tc(p.kv_kind, p.heads / p.kv_heads <= 4);
   const size_t smem = tc_smem(p.kv_kind);
   cuda_check(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "tree_decode_tc smem attr");
   void* args[] = {(void*)&map_k, (void*)&map_v, (void*)&p};

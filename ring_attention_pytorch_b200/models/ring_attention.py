@@ -37,6 +37,7 @@ from ring_attention_pytorch_b200.parallel.distributed import (
     split_by_rank,
 )
 from ring_attention_pytorch_b200.parallel.layout import make_position_map
+from ring_attention_pytorch_b200.utils.validate import typecheck
 
 
 def sm100_kernels_usable(dim_head: int = 64) -> bool:
@@ -58,6 +59,7 @@ def cast_tuple(t, length: int = 1):
 # rotary embeddings aware of the sequence layout (reference ring_attention.py:102-172)
 # ------------------------------------------------------------------------------------------------
 class RingRotaryEmbedding(Module):
+    @typecheck
     def __init__(self, dim: int, ring: bool = False, striped: bool = False, buckets: int = 1, theta: float = 10000):
         super().__init__()
         self.ring = ring
@@ -231,6 +233,7 @@ class RingAttention(Module):
     """Multi-head / grouped-query attention whose sequence dimension may be sharded over a ring of ranks
     (reference ring_attention.py:283-466, same constructor and forward signature)."""
 
+    @typecheck
     def __init__(
         self,
         dim: int,
@@ -358,6 +361,7 @@ class RingAttention(Module):
 class RingTransformer(Module):
     """Small decoder/encoder stack for end-to-end tests and benchmarks (reference ring_attention.py:488-685)."""
 
+    @typecheck
     def __init__(
         self,
         *,

@@ -32,9 +32,19 @@ def load(build_if_missing: bool = True) -> bool:
             return True
         try:
             if not _SO.exists() and build_if_missing and os.environ.get("RAB_NO_BUILD", "0") != "1":
+                # every rank of a torchrun / mp.spawn launch gets here at the same time on a fresh checkout: one process
+                # builds under an exclusive file lock, the others wait for it and then find the finished object
+                import fcntl
+
                 from ring_attention_pytorch_b200 import build as _build
 
-                _build.build(verbose=False)
+                with open(str(_PKG / ".build.lock"), "w") as lock:
+                    fcntl.flock(lock, fcntl.LOCK_EX)
+                    try:
+                        if not _SO.exists():
+                            _build.build(verbose=False)
+                    finally:
+                        fcntl.flock(lock, fcntl.LOCK_UN)
             torch.ops.load_library(str(_SO))
             _loaded = True
         except Exception as e:  # pragma: no cover - depends on toolchain

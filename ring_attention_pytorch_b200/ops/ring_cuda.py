@@ -46,6 +46,7 @@ from ring_attention_pytorch_b200.parallel.distributed import default, exists, ge
 from ring_attention_pytorch_b200.parallel.layout import make_position_map, ring_hop_owners, ring_query_owners
 from ring_attention_pytorch_b200.parallel.symm import get_workspace
 from ring_attention_pytorch_b200.utils.timing import nvtx_range
+from ring_attention_pytorch_b200.utils.validate import check_attention_inputs, typecheck
 
 # counts launches of our own kernels (bench.py reports it as gpu_launches)
 LAUNCHES = {"count": 0}
@@ -334,6 +335,7 @@ ring_flash_attn_cuda_ = RingFlashAttentionCUDAFunction.apply
 
 
 @torch.autocast("cuda", enabled=False)
+@typecheck
 def ring_flash_attn_cuda(
     q: Tensor,
     k: Tensor,
@@ -354,6 +356,7 @@ def ring_flash_attn_cuda(
     accepted for signature parity; tiling is fixed by the kernel (128 x 128).  ``rotary_freqs`` ([n, d] or [n, d/2]
     fp32 angles, e.g. the output of ``RingRotaryEmbedding``): rotary embedding of q and k applied inside the op's pack
     kernels instead of by eager PyTorch passes."""
+    check_attention_inputs(q, k, v, mask, name="ring_flash_attn_cuda", max_head_dim=128)
     return ring_flash_attn_cuda_(q, k, v, mask, causal, bucket_size, ring_reduce_col, striped_ring_attn,
                                  max_lookback_seq_len, ring_size, softclamp_qk_sim, softclamp_value, layout,
                                  rotary_freqs)

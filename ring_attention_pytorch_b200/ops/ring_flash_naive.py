@@ -24,6 +24,7 @@ from torch.autograd import Function
 from ring_attention_pytorch_b200.parallel.distributed import default, exists, get_rank, get_world_size, is_distributed
 from ring_attention_pytorch_b200.parallel.layout import PositionMap, make_position_map, ring_hop_owners
 from ring_attention_pytorch_b200.parallel.ring import all_ring_pass, null_ring_pass, ring_pass
+from ring_attention_pytorch_b200.utils.validate import check_attention_inputs, typecheck
 
 EPSILON = 1e-10
 
@@ -229,6 +230,7 @@ class RingFlashAttentionFunction(Function):
 ring_flash_attn_ = RingFlashAttentionFunction.apply
 
 
+@typecheck
 def ring_flash_attn(
     q: Tensor,
     k: Tensor,
@@ -245,5 +247,6 @@ def ring_flash_attn(
     layout: Optional[str] = None,
 ) -> Tensor:
     """Reference-compatible signature (ring_flash_attention.py:391-406) + ``layout`` ('plain'|'striped'|'zigzag')."""
+    check_attention_inputs(q, k, v, mask, name="ring_flash_attn")
     return ring_flash_attn_(q, k, v, mask, causal, bucket_size, ring_reduce_col, striped_ring_attn,
                             max_lookback_seq_len, ring_size, softclamp_qk_sim, softclamp_value, layout)

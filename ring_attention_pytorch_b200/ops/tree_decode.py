@@ -22,6 +22,7 @@ import torch.distributed as dist
 from torch import Tensor
 
 from ring_attention_pytorch_b200.parallel.distributed import default, exists, get_rank, get_world_size, is_distributed
+from ring_attention_pytorch_b200.utils.validate import typecheck
 
 
 def _local_attention(q: Tensor, k: Tensor, v: Tensor):
@@ -39,6 +40,7 @@ def _local_attention(q: Tensor, k: Tensor, v: Tensor):
 
 
 @torch.no_grad()
+@typecheck
 def tree_attn_decode(
     q: Tensor,
     k: Optional[Tensor] = None,

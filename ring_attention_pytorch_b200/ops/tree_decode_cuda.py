@@ -165,7 +165,8 @@ def tree_decode_cuda(
     tc = CONFIG["tensor_core"]
     # a 128-key tile of the tensor-core kernel must lie inside one scale block
     use_tc = tc in ("auto", True, "on") and d == 128 and n >= 128 and scale_block_keys % 128 == 0
-    groups = b * hk * ((g + 15) // 16 if use_tc else (g + 3) // 4)
+    gm = (4 if g <= 4 else 16) if use_tc else 4  # query heads per work unit (tensor-core kernel: template bound GM)
+    groups = b * hk * ((g + gm - 1) // gm)
     resident = int(ops.tree_decode_max_ctas(d, kv_kind, use_tc))
     splits = _choose_splits(n, groups, resident)
     buf = _buffers(b * h, d, dev)

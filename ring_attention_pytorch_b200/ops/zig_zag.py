@@ -21,6 +21,7 @@ from torch import Tensor
 
 from ring_attention_pytorch_b200.parallel.distributed import AllGather, get_rank, get_world_size, is_distributed
 from ring_attention_pytorch_b200.parallel.layout import make_position_map
+from ring_attention_pytorch_b200.utils.validate import typecheck
 
 ShardOutput = namedtuple("ShardOutput", ["local_sequence", "query_positions", "key_value_positions"])
 
@@ -64,6 +65,7 @@ def zig_zag_shard(t: Tensor, all_gather_batch: bool = False):
     return ShardOutput(local, q_indices, kv_indices), inverse
 
 
+@typecheck
 def zig_zag_attn(
     q: Tensor,
     k: Tensor,

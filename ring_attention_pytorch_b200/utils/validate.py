@@ -15,10 +15,14 @@ import torch
 from torch import Tensor
 
 try:  # pragma: no cover - exercised implicitly by every decorated call
+    from beartype import BeartypeConf
     from beartype import beartype as _beartype
 
+    # PEP 484 numeric tower: an int is accepted where a float is annotated (``theta=10000``, ``softclamp_value=50``)
+    _checked = _beartype(conf=BeartypeConf(is_pep484_tower=True))
+
     def typecheck(fn):
-        return _beartype(fn)
+        return _checked(fn)
 
     HAVE_BEARTYPE = True
 except Exception:  # noqa: BLE001

@@ -487,6 +487,9 @@ CASES = {
     "perfbwd_causal_16k": lambda: case_perf_bwd(),
     "perfbwd_full_8k": lambda: case_perf_bwd(n=8192, causal=False),
     "perfbwd_causal_64k_h8": lambda: case_perf_bwd(n=65536, h=8, iters=3),
+    "dec_small_tc": lambda: case_perf_decode(batch=2, h=8, hk=2, n=512, iters=1),
+    "dec_small_tc_fp8": lambda: case_perf_decode(batch=2, h=8, hk=2, n=512, iters=1, fp8=True),
+    "dec_small_cudacore": lambda: case_perf_decode(batch=2, h=8, hk=2, n=512, iters=1, tensor_core=False),
     "perfdec_bf16": lambda: case_perf_decode(),
     "perfdec_fp8": lambda: case_perf_decode(fp8=True),
     "perfdec_mha_b32": lambda: case_perf_decode(batch=32, h=32, hk=32, n=8192),

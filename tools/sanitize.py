@@ -47,6 +47,9 @@ def main():
                     code = -1
                 m = re.search(r"ERROR SUMMARY: (\d+) error", out)
                 errors = int(m.group(1)) if m else None
+                if errors is None:  # racecheck prints "RACECHECK SUMMARY: N hazards displayed (E errors, W warnings)"
+                    m = re.search(r"RACECHECK SUMMARY: (\d+) hazard", out)
+                    errors = int(m.group(1)) if m else None
                 ok_line = next((l[7:] for l in out.splitlines() if l.startswith("RESULT ")), "")
                 status = "timeout" if code == -1 else ("clean" if errors == 0 and code == 0 else "ERRORS")
                 line = f"[{tool}] {case}: {status} (errors={errors}, exit={code}, {time.time() - t0:.0f}s) {ok_line}"
