@@ -48,7 +48,7 @@ struct TcSmem {
   uint64_t o_done;
   float red[4][TC_NH];   // cross-warp reductions (tile maxima, row sums)
   float qscale[TC_NH];   // fp8: per-head dequantisation scale of the quantised query
-  int unit;
+  int unit, unit_next;
   uint32_t last;
   uint32_t tmem_base;
 };
@@ -160,11 +160,21 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
   uint32_t n_tile = 0;   // tiles of this CTA so far: stage = n_tile % NST, S / P buffer = n_tile & 1
   uint32_t n_unit = 0;
 
+  // The work queue is read one unit AHEAD: at the end of a unit the TMA producer already streams the first tiles of the
+  // next one, so the shared-memory ring does not drain while the warpgroup runs the epilogue and builds the next Q^T.
+  uint32_t n_prod = 0;    // tiles issued by the producer so far (runs ahead of n_tile by the prefetched tiles)
+  int pre_issued = 0;     // tiles of the CURRENT unit that were issued during the previous unit's tail
+  bool first = true;
   while (true) {
     __syncthreads();
-    if (tid == 0) sm.unit = (int)atomicAdd(&ctr[0], 1u);
+    if (tid == 0) {
+      sm.unit = first ? (int)atomicAdd(&ctr[0], 1u) : sm.unit_next;
+      sm.unit_next = (int)atomicAdd(&ctr[0], 1u);
+    }
+    first = false;
     __syncthreads();
     const int unit = sm.unit;
+    const int unit_next = sm.unit_next;
     if (unit >= total_units) break;
     const int split = unit % p.splits;
     const int grp = unit / p.splits;
@@ -228,19 +238,31 @@ tree_decode_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
     if (warp == 0) {
       // =============================================== TMA producer ===============================================
       if (lane == 0) {
-        for (int t = 0; t < ntiles; ++t) {
-          const uint32_t n = n_tile + t, st = n % NST, ph = (n / NST) & 1;
-          const int key0 = k0 + t * TC_TILE;
+        auto issue_tile = [&](int bhk_, int key0) {
+          const uint32_t st = n_prod % NST, ph = (n_prod / NST) & 1;
           mbar_wait(&sm.k_empty[st], ph ^ 1, 2000 + st);
           mbar_expect_tx(&sm.k_full[st], Smem::TILE_BYTES);
 #pragma unroll
-          for (int s = 0; s < NSUB; ++s)
-            tma_load_3d(sm.k[st] + s * SUBK, &map_k, &sm.k_full[st], s * (KV8 ? 128 : 64), key0, bhk);
+          for (int s2 = 0; s2 < NSUB; ++s2)
+            tma_load_3d(sm.k[st] + s2 * SUBK, &map_k, &sm.k_full[st], s2 * (KV8 ? 128 : 64), key0, bhk_);
           mbar_wait(&sm.v_empty[st], ph ^ 1, 2010 + st);
           mbar_expect_tx(&sm.v_full[st], Smem::TILE_BYTES);
 #pragma unroll
-          for (int s = 0; s < NSUB; ++s)
-            tma_load_3d(sm.v[st] + s * SUBK, &map_v, &sm.v_full[st], s * (KV8 ? 128 : 64), key0, bhk);
+          for (int s2 = 0; s2 < NSUB; ++s2)
+            tma_load_3d(sm.v[st] + s2 * SUBK, &map_v, &sm.v_full[st], s2 * (KV8 ? 128 : 64), key0, bhk_);
+          n_prod++;
+        };
+        for (int t = pre_issued; t < ntiles; ++t) issue_tile(bhk, k0 + t * TC_TILE);
+        // run ahead into the next unit: at most NST tiles, whose slots free up as THIS unit's last tiles are consumed
+        pre_issued = 0;
+        if (unit_next < total_units) {
+          const int split_n = unit_next % p.splits;
+          const int bhk_n = (unit_next / p.splits) / zchunks;
+          const int k0_n = split_n * per, k1_n = min(p.n, k0_n + per);
+          const int nt_n = k1_n > k0_n ? (k1_n - k0_n + TC_TILE - 1) / TC_TILE : 0;
+          const int ahead = min(nt_n, NST);
+          for (int t = 0; t < ahead; ++t) issue_tile(bhk_n, k0_n + t * TC_TILE);
+          pre_issued = ahead;
         }
       }
     } else if (warp == 1) {

@@ -14,6 +14,9 @@ from typing import Optional
 import torch
 from torch import Tensor
 
+from ring_attention_pytorch_b200.utils.tensor_typing import Bool, Float
+from ring_attention_pytorch_b200.utils.validate import typecheck
+
 
 def softclamp(t: Tensor, value: float) -> Tensor:
     return (t / value).tanh() * value
@@ -82,11 +85,12 @@ def attention_with_positions(
     return out
 
 
+@typecheck
 def default_attention(
-    q: Tensor,
-    k: Tensor,
-    v: Tensor,
-    mask: Optional[Tensor] = None,
+    q: Float["b i h d"],
+    k: Float["b j hk d"],
+    v: Float["b j hk d"],
+    mask: Optional[Bool["b j"]] = None,
     causal: bool = False,
     softclamp_qk_sim: bool = False,
     softclamp_value: float = 50.0,

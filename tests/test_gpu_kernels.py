@@ -613,3 +613,35 @@ def test_rotary_module_launches_no_eager_rotary_kernels():
     names = [e.key for e in prof.key_averages()]
     assert any("rotary_kernel" in nme for nme in names), names
     assert not any(("sin" in nme.lower() or "cos" in nme.lower()) and "rotary_kernel" not in nme for nme in names), names
+
+
+@pytest.mark.parametrize("fp8", [False, True])
+def test_tree_decode_is_cuda_graph_capturable(fp8):
+    """A decode step allocates nothing and keeps its counters / epoch in device memory: capture once, replay with new
+    queries, compare every replay with the dense oracle."""
+    from ring_attention_pytorch_b200.ops import tree_decode_cuda as tdc
+    from ring_attention_pytorch_b200.ops.tree_decode_cuda import tree_decode_cuda
+
+    tdc.CONFIG["tensor_core"] = "auto"
+    torch.manual_seed(0)
+    b, h, hk, n, d = 4, 16, 4, 2048, 128
+    q = torch.randn(b, h, 1, d, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(b, hk, n, d, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(b, hk, n, d, device="cuda", dtype=torch.bfloat16)
+    ks = vs = None
+    kk, vv = k, v
+    if fp8:
+        kk, vv = k.to(torch.float8_e4m3fn), v.to(torch.float8_e4m3fn)
+        ks = vs = torch.ones(b * hk, device="cuda")
+    out = torch.empty_like(q)
+    tree_decode_cuda(q, kk, vv, dim_v=d, k_scale=ks, v_scale=vs, out=out)  # warm-up: creates the cached buffers
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        tree_decode_cuda(q, kk, vv, dim_v=d, k_scale=ks, v_scale=vs, out=out)
+    for it in range(3):
+        q.copy_(torch.randn_like(q))
+        graph.replay()
+        torch.cuda.synchronize()
+        ref = _dense_decode(q, kk.float(), vv.float())
+        assert (out.float() - ref).abs().max() < (6e-2 if fp8 else 2e-2), it
