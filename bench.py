@@ -54,6 +54,8 @@ def parse_args():
                     help="reference arm only: cap the timed steps so that one timed loop stays inside this budget")
     ap.add_argument("--probe-device", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--fwd-only", action="store_true", help="diagnostic only (not a valid headline number)")
+    ap.add_argument("--memory", default="gather", choices=["gather", "ring"],
+                    help="ring_cuda.CONFIG['memory']: 'ring' = per-hop launches against a 2-slot K/V window (O(n/W) workspace)")
     return ap.parse_args()
 
 
@@ -248,6 +250,8 @@ def main():
         ref_env = probe_reference_backward(local_rank)
     else:
         from ring_attention_pytorch_b200.ops import ring_cuda
+
+        ring_cuda.CONFIG["memory"] = args.memory
 
         def attn(q, k, v, bucket):
             return ring_cuda.ring_flash_attn_cuda(q, k, v, None, True, bucket, ring, ring, None, world)
@@ -515,6 +519,7 @@ def main():
                 "flops": "fwd 4*b*h*S^2*d*0.5, bwd 2.5x fwd (algorithmic 5-GEMM count)",
                 "l2": "inputs larger than L2 (no flush needed)",
                 "fwd_only": bool(args.fwd_only),
+                "memory": args.memory,
                 **({"reference_env": ref_env} if ref_env else {}),
                 **({"steps_requested": args.steps} if main_row["steps"] != args.steps else {}),
             },

@@ -47,6 +47,7 @@ struct FwdSmem {
   uint64_t q_full[2], q_empty[2];
   uint64_t kv_full[NSLOT], kv_empty[NSLOT];
   uint64_t s_full[2], p_ready[2], o_done[2], epi_done[2];
+  uint64_t item_go[2], o_ready[2];  // hop-at-a-time mode: issuer started the item / the carried O sits in TMEM
   uint64_t fetch_full[2];
   uint32_t tmem_base;
 };
@@ -116,7 +117,7 @@ __device__ __forceinline__ void producer_role(FwdSmem<D>& sm, const AttnFwdParam
   const int lane = lane_id();
   uint32_t n_slot = 0;
   uint32_t items_t[2] = {0, 0};
-  uint32_t ready_mask = 1u << p.rank;
+  uint32_t ready_mask = p.all_ready ? 0xffffffffu : (1u << p.rank);
   const int total = num_items(p);
   for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
     Item it;
@@ -214,11 +215,21 @@ __device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p,
       if (it.tvalid[t]) mbar_wait(&sm.q_full[t], items_t[t] & 1, 200 + t);
     tc_fence_after();
 
+    const bool carry = p.carry_in != 0;
+    if (carry) {
+      // the warpgroups may load the carried state of this item now (keeps them in lock step with this warp: they
+      // can never run two items ahead, so the parity waits on o_ready stay unambiguous)
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (it.tvalid[t] && elect_one()) mbar_arrive(&sm.item_go[t]);
+      __syncwarp();
+    }
     FwdScan scan;
     init_scan(scan, p, it);
     ScanTile cur, nxt;
     bool has = scan.next(lane, cur);
-    bool pv_started[2] = {false, false};
+    bool pv_started[2] = {carry, carry};   // a carried O is accumulated into from the first P V on
+    bool o_waited[2] = {false, false};
     if (has) {
       const uint32_t ks = (2 * n_kv) % NSLOT, kph = ((2 * n_kv) / NSLOT) & 1;
       mbar_wait(&sm.kv_full[ks], kph, 210);
@@ -239,7 +250,13 @@ __device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p,
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (cur.need[t]) {
-          if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 230 + t);
+          if (!o_waited[t]) {
+            // the O block of this Q tile is ours: the previous item's epilogue has drained it, or (hop mode) the
+            // warpgroup has loaded the carried accumulator into it
+            if (carry) mbar_wait(&sm.o_ready[t], items_t[t] & 1, 232 + t);
+            else mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 230 + t);
+            o_waited[t] = true;
+          }
           mbar_wait(&sm.p_ready[t], cnt_p[t] & 1, 240 + t);
           tc_fence_after();
           const uint32_t ot = t ? o_tm1 : o_tm0, st = t ? s_tm1 : s_tm0;
@@ -272,7 +289,10 @@ __device__ __forceinline__ void mma_role(FwdSmem<D>& sm, const AttnFwdParams& p,
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       if (!it.tvalid[t]) continue;
-      if (!pv_started[t]) mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 260 + t);
+      if (!o_waited[t]) {
+        if (carry) mbar_wait(&sm.o_ready[t], items_t[t] & 1, 262 + t);
+        else mbar_wait(&sm.epi_done[t], (items_t[t] & 1) ^ 1, 260 + t);
+      }
       umma_commit_w(&sm.q_empty[t]);
       items_t[t]++;
     }
@@ -371,6 +391,7 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
   uint64_t* const o_done = &sm.o_done[0] + t;
   uint64_t* const epi_done = &sm.epi_done[0] + t;
   uint32_t cnt = 0;
+  uint32_t n_items = 0;  // valid items of this warpgroup so far (hop mode barriers)
 
   const bool clamp = p.softclamp > 0.f;
   const float mul = clamp ? 1.f : p.scale * kLog2e;
@@ -392,6 +413,34 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
     float l = 0.f;
     bool have_o = false;
     uint32_t cnt_item = 0;
+    if (p.carry_in) {
+      // hop-at-a-time mode: O / m / l of this row continue from the previous hop's launch.  The O block is free (this
+      // thread drained it in the previous item's epilogue); the issuer waits on o_ready before its first P V.
+      mbar_wait(&sm.item_go[t], n_items & 1, 430 + t);
+      const size_t mlrow = ((size_t)it.b * p.heads + it.h) * p.n_q + (row_ok ? grow : 0);
+      m_used = row_ok ? p.carry_ml[mlrow] : -INFINITY;
+      l = row_ok ? p.carry_ml[(size_t)p.batch * p.heads * p.n_q + mlrow] : 0.f;
+      const float4* crow = reinterpret_cast<const float4*>(
+          p.carry_o + (((size_t)it.b * p.n_q + (row_ok ? grow : 0)) * p.heads + it.h) * D);
+#pragma unroll 1
+      for (int c = 0; c < D; c += 32) {
+        uint32_t orr[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 x = row_ok ? crow[c / 4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          orr[4 * i + 0] = __float_as_uint(x.x);
+          orr[4 * i + 1] = __float_as_uint(x.y);
+          orr[4 * i + 2] = __float_as_uint(x.z);
+          orr[4 * i + 3] = __float_as_uint(x.w);
+        }
+        tmem_st32(o_tm + c, orr);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&sm.o_ready[t]);
+      have_o = true;
+    }
+    n_items++;
 
     FwdScan scan;
     init_scan(scan, p, it);
@@ -522,13 +571,42 @@ __device__ __forceinline__ void softmax_role(FwdSmem<D>& sm, const AttnFwdParams
       mbar_wait(o_done, (cnt - 1) & 1, 410 + t);
       tc_fence_after();
     }
+    if (p.carry_out) {
+      // hand the un-normalised state to the next hop's launch
+      float4* crow = reinterpret_cast<float4*>(p.carry_o + (((size_t)it.b * p.n_q + (row_ok ? grow : 0)) * p.heads + it.h) * D);
+#pragma unroll 1
+      for (int c = 0; c < D; c += 32) {
+        uint32_t orr[32];
+        if (cnt_item > 0 || p.carry_in) {
+          tmem_ld32(o_tm + c, orr);
+          tc_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) orr[i] = 0u;
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            crow[c / 4 + i] = make_float4(__uint_as_float(orr[4 * i]), __uint_as_float(orr[4 * i + 1]),
+                                          __uint_as_float(orr[4 * i + 2]), __uint_as_float(orr[4 * i + 3]));
+        }
+      }
+      if (row_ok) {
+        const size_t mlrow = ((size_t)it.b * p.heads + it.h) * p.n_q + grow;
+        p.carry_ml[mlrow] = m_used;
+        p.carry_ml[(size_t)p.batch * p.heads * p.n_q + mlrow] = l;
+      }
+      tc_fence_before();
+      mbar_arrive(epi_done);
+      continue;
+    }
     const float inv = l > 0.f ? 1.f / l : 0.f;
     uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
                                            (((size_t)it.b * p.n_q + (row_ok ? grow : 0)) * p.heads + it.h) * D);
 #pragma unroll 1
     for (int c = 0; c < D; c += 32) {
       uint32_t orr[32];
-      if (cnt_item > 0) {
+      if (cnt_item > 0 || p.carry_in) {
         tmem_ld32(o_tm + c, orr);
         tc_wait_ld();
       } else {
@@ -573,6 +651,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_init(&sm.o_done[i], 1);
       mbar_init(&sm.epi_done[i], 128);
       mbar_init(&sm.fetch_full[i], 1);
+      mbar_init(&sm.item_go[i], 1);
+      mbar_init(&sm.o_ready[i], 128);
     }
     for (int i = 0; i < NSLOT; ++i) {
       mbar_init(&sm.kv_full[i], 1);

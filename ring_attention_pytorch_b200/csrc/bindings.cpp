@@ -120,24 +120,42 @@ Tensor umma_rate(int64_t mode, int64_t n, int64_t reps, int64_t alt, int64_t cta
   return out;
 }
 
-std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& kv_buf, at::IntArrayRef peer_ptrs,
-                                    const Tensor& ready, const c10::optional<Tensor>& kmask_bits,
-                                    int64_t kv_heads, int64_t rank, bool causal, int64_t window, double scale,
-                                    double softclamp, int64_t pos_stride, int64_t seg_len, at::IntArrayRef base0,
-                                    at::IntArrayRef base1, int64_t q_pos_offset, at::IntArrayRef hop_owner) {
+// Hop mode (memory = "ring"): kv_buf holds ONE owner's slot ([1, 2, b*hk, n_k, d]); the launch visits that owner only
+// and carries the online-softmax state (un-normalised O, running max / sum) in fp32 buffers between launches.
+struct FwdHop {
+  int owner = -1;        // -1: single-launch mode
+  int world = 0;
+  float* carry_o = nullptr;
+  float* carry_ml = nullptr;
+  bool carry_in = false, carry_out = false;
+};
+
+std::tuple<Tensor, Tensor> attn_fwd_impl(const Tensor& q, const Tensor& kv_buf, at::IntArrayRef peer_ptrs,
+                                         const c10::optional<Tensor>& ready_opt,
+                                         const c10::optional<Tensor>& kmask_bits, int64_t kv_heads, int64_t rank,
+                                         bool causal, int64_t window, double scale, double softclamp,
+                                         int64_t pos_stride, int64_t seg_len, at::IntArrayRef base0,
+                                         at::IntArrayRef base1, int64_t q_pos_offset, at::IntArrayRef hop_owner,
+                                         const FwdHop& hop) {
   check_16bit(q, "q");
   check_16bit(kv_buf, "kv_buf");
+  const bool hop_mode = hop.owner >= 0;
   TORCH_CHECK(q.dim() == 4 && q.is_contiguous(), "q must be contiguous [b, n, h, d]");
   TORCH_CHECK(kv_buf.dim() == 5 && kv_buf.is_contiguous(), "kv_buf must be contiguous [world, 2, b*hk, n_k, d]");
   TORCH_CHECK(kv_buf.scalar_type() == q.scalar_type());
   const int b = q.size(0), n_q = q.size(1), h = q.size(2), d = q.size(3);
-  const int world = kv_buf.size(0), n_k = kv_buf.size(3);
+  const int world = hop_mode ? hop.world : (int)kv_buf.size(0), n_k = kv_buf.size(3);
   TORCH_CHECK(kv_buf.size(1) == 2 && kv_buf.size(2) == b * kv_heads && kv_buf.size(4) == d);
   TORCH_CHECK(d == 64 || d == 128, "head dim must be 64 or 128");
   TORCH_CHECK(h % kv_heads == 0);
-  TORCH_CHECK(world <= rab::kMaxWorld && (int)peer_ptrs.size() == world);
-  TORCH_CHECK(ready.is_cuda() && ready.scalar_type() == at::kInt && ready.numel() >= world);
-  TORCH_CHECK(hop_owner.size() >= 1 && (int)hop_owner.size() <= world && hop_owner[0] == rank);
+  TORCH_CHECK(world <= rab::kMaxWorld);
+  if (hop_mode) {
+    TORCH_CHECK(kv_buf.size(0) == 1 && hop.owner < world && hop_owner.size() == 1 && hop_owner[0] == hop.owner);
+  } else {
+    TORCH_CHECK((int)peer_ptrs.size() == world && ready_opt.has_value());
+    TORCH_CHECK(ready_opt->is_cuda() && ready_opt->scalar_type() == at::kInt && ready_opt->numel() >= world);
+    TORCH_CHECK(hop_owner.size() >= 1 && (int)hop_owner.size() <= world && hop_owner[0] == rank);
+  }
   c10::cuda::CUDAGuard guard(q.device());
   auto stream = at::cuda::getCurrentCUDAStream();
 
@@ -164,13 +182,24 @@ std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& kv_buf, at::I
     p.kmask_bits = reinterpret_cast<const uint32_t*>(km.data_ptr<int>());
     p.kmask_words = km.size(2);
   }
-  p.kv_local = reinterpret_cast<uint8_t*>(kv_buf.data_ptr());
   p.slot_bytes = 2ull * b * kv_heads * n_k * d * 2;
-  for (int i = 0; i < world; ++i)
-    p.kv_peer[i] = peer_ptrs[i] ? reinterpret_cast<const uint8_t*>(peer_ptrs[i]) : p.kv_local + i * p.slot_bytes;
-  p.ready = reinterpret_cast<uint32_t*>(ready.data_ptr<int>());
-  rab::cuda_check(cudaMemsetAsync(p.ready, 0, sizeof(uint32_t) * world, stream), "ready memset");
-  p.fetch_times = (g_fetch_times != nullptr && g_fetch_times_rows >= sm_count()) ? g_fetch_times : nullptr;
+  // the kernels address owner o's K / V at slot o of the buffer; in hop mode the one slot we were given IS slot
+  // `owner`, so the base is shifted down by owner slots (only that slot is ever dereferenced)
+  uint8_t* kv_base = reinterpret_cast<uint8_t*>(kv_buf.data_ptr()) - (hop_mode ? hop.owner * p.slot_bytes : 0);
+  p.kv_local = kv_base;
+  if (hop_mode) {
+    p.all_ready = 1;
+    p.carry_o = hop.carry_o;
+    p.carry_ml = hop.carry_ml;
+    p.carry_in = hop.carry_in;
+    p.carry_out = hop.carry_out;
+  } else {
+    for (int i = 0; i < world; ++i)
+      p.kv_peer[i] = peer_ptrs[i] ? reinterpret_cast<const uint8_t*>(peer_ptrs[i]) : p.kv_local + i * p.slot_bytes;
+    p.ready = reinterpret_cast<uint32_t*>(ready_opt->data_ptr<int>());
+    rab::cuda_check(cudaMemsetAsync(p.ready, 0, sizeof(uint32_t) * world, stream), "ready memset");
+    p.fetch_times = (g_fetch_times != nullptr && g_fetch_times_rows >= sm_count()) ? g_fetch_times : nullptr;
+  }
 
   // Q: [b, n, h, d] -> dims (d, h, n, b), box (64, 1, 128, 1)
   uint64_t qdims[4] = {(uint64_t)d, (uint64_t)h, (uint64_t)n_q, (uint64_t)b};
@@ -181,7 +210,7 @@ std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& kv_buf, at::I
   uint64_t kdims[4] = {(uint64_t)d, (uint64_t)n_k, (uint64_t)b * kv_heads, (uint64_t)2 * world};
   uint64_t kstr[3] = {(uint64_t)d * 2, (uint64_t)n_k * d * 2, (uint64_t)b * kv_heads * n_k * d * 2};
   uint32_t kbox[4] = {64, 128, 1, 1};
-  CUtensorMap map_kv = rab::make_tmap_bf16(kv_buf.data_ptr(), 4, kdims, kstr, kbox, rab::TmapSwizzle::B128);
+  CUtensorMap map_kv = rab::make_tmap_bf16(kv_base, 4, kdims, kstr, kbox, rab::TmapSwizzle::B128);
 
   if (d == 128) {
     rab::launch_attn_fwd<128>(map_q, map_kv, p, sm_count(), stream);
@@ -189,6 +218,42 @@ std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& kv_buf, at::I
     rab::launch_attn_fwd<64>(map_q, map_kv, p, sm_count(), stream);
   }
   return {o, lse};
+}
+
+std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& kv_buf, at::IntArrayRef peer_ptrs,
+                                    const Tensor& ready, const c10::optional<Tensor>& kmask_bits,
+                                    int64_t kv_heads, int64_t rank, bool causal, int64_t window, double scale,
+                                    double softclamp, int64_t pos_stride, int64_t seg_len, at::IntArrayRef base0,
+                                    at::IntArrayRef base1, int64_t q_pos_offset, at::IntArrayRef hop_owner) {
+  return attn_fwd_impl(q, kv_buf, peer_ptrs, ready, kmask_bits, kv_heads, rank, causal, window, scale, softclamp,
+                       pos_stride, seg_len, base0, base1, q_pos_offset, hop_owner, FwdHop{});
+}
+
+// One ring hop of the forward: q against owner `owner`'s K / V slot.  carry_o fp32 [b, n_q, h, d] and carry_ml fp32
+// [2, b*h, n_q] hold the online-softmax state between hops; the launch with carry_out = false writes the final O / lse.
+std::tuple<Tensor, Tensor> attn_fwd_hop(const Tensor& q, const Tensor& kv_slot, int64_t owner, int64_t world,
+                                        Tensor carry_o, Tensor carry_ml, bool carry_in, bool carry_out,
+                                        const c10::optional<Tensor>& kmask_bits, int64_t kv_heads, int64_t rank,
+                                        bool causal, int64_t window, double scale, double softclamp,
+                                        int64_t pos_stride, int64_t seg_len, at::IntArrayRef base0,
+                                        at::IntArrayRef base1, int64_t q_pos_offset) {
+  TORCH_CHECK(q.dim() == 4);
+  const int64_t b = q.size(0), n_q = q.size(1), h = q.size(2), d = q.size(3);
+  TORCH_CHECK(carry_o.is_cuda() && carry_o.scalar_type() == at::kFloat && carry_o.is_contiguous() &&
+              carry_o.numel() == b * n_q * h * d, "carry_o must be fp32 [b, n_q, h, d]");
+  TORCH_CHECK(carry_ml.is_cuda() && carry_ml.scalar_type() == at::kFloat && carry_ml.is_contiguous() &&
+              carry_ml.numel() == 2 * b * h * n_q, "carry_ml must be fp32 [2, b*h, n_q]");
+  TORCH_CHECK(owner >= 0 && owner < world);
+  FwdHop hop;
+  hop.owner = (int)owner;
+  hop.world = (int)world;
+  hop.carry_o = carry_o.data_ptr<float>();
+  hop.carry_ml = carry_ml.data_ptr<float>();
+  hop.carry_in = carry_in;
+  hop.carry_out = carry_out;
+  const int64_t owners[1] = {owner};
+  return attn_fwd_impl(q, kv_slot, {}, c10::nullopt, kmask_bits, kv_heads, rank, causal, window, scale, softclamp,
+                       pos_stride, seg_len, base0, base1, q_pos_offset, at::IntArrayRef(owners, 1), hop);
 }
 
 
@@ -331,12 +396,16 @@ std::tuple<Tensor, Tensor> attn_bwd_ring(const Tensor& qdo, const Tensor& kv_buf
                                          int64_t kv_heads, int64_t rank, bool causal, int64_t window, double scale,
                                          double softclamp, int64_t pos_stride, int64_t seg_len, at::IntArrayRef base0,
                                          at::IntArrayRef base1, int64_t q_pos_offset, at::IntArrayRef hop_owner,
-                                         at::IntArrayRef dkv_acc_ptrs, int64_t nk_pad) {
+                                         at::IntArrayRef dkv_acc_ptrs, int64_t nk_pad, int64_t world_size,
+                                         int64_t slot_owner) {
+  // slot_owner >= 0 (memory = "ring"): kv_buf is ONE owner's slot [1, 2, b*hk, n_k, d] of a `world_size` ring and
+  // hop_owner == [slot_owner]; dq_acc and the dK / dV accumulators keep adding up across the per-hop launches
   check_16bit(qdo, "qdo");
   check_16bit(kv_buf, "kv_buf");
   TORCH_CHECK(qdo.is_contiguous() && kv_buf.is_contiguous() && stat.is_contiguous() && dq_acc.is_contiguous());
   TORCH_CHECK(kv_buf.dim() == 5 && qdo.dim() == 4 && stat.dim() == 3 && dq_acc.dim() == 3);
-  const int world = kv_buf.size(0), n_k = kv_buf.size(3), d = kv_buf.size(4);
+  const bool hop_mode = slot_owner >= 0;
+  const int world = hop_mode ? (int)world_size : (int)kv_buf.size(0), n_k = kv_buf.size(3), d = kv_buf.size(4);
   const int n_q = qdo.size(2), n_pad = stat.size(2);
   TORCH_CHECK(d == 128, "attn_bwd_ring: head dim 128 only");
   TORCH_CHECK(qdo.size(0) == 2 && qdo.size(1) == batch * heads && qdo.size(3) == d);
@@ -345,8 +414,12 @@ std::tuple<Tensor, Tensor> attn_bwd_ring(const Tensor& qdo, const Tensor& kv_buf
   TORCH_CHECK(dq_acc.scalar_type() == at::kFloat && dq_acc.size(0) == batch * heads && dq_acc.size(1) == n_pad &&
               dq_acc.size(2) == d);
   TORCH_CHECK(kv_buf.size(1) == 2 && kv_buf.size(2) == batch * kv_heads && heads % kv_heads == 0);
-  TORCH_CHECK(world <= rab::kMaxWorld && hop_owner.size() >= 1 && (int)hop_owner.size() <= world &&
-              hop_owner[0] == rank);
+  TORCH_CHECK(world <= rab::kMaxWorld && hop_owner.size() >= 1 && (int)hop_owner.size() <= world);
+  if (hop_mode) {
+    TORCH_CHECK(kv_buf.size(0) == 1 && slot_owner < world && hop_owner.size() == 1 && hop_owner[0] == slot_owner);
+  } else {
+    TORCH_CHECK(hop_owner[0] == rank);
+  }
   c10::cuda::CUDAGuard guard(kv_buf.device());
   auto stream = at::cuda::getCurrentCUDAStream();
 
@@ -384,7 +457,9 @@ std::tuple<Tensor, Tensor> attn_bwd_ring(const Tensor& qdo, const Tensor& kv_buf
   uint64_t kdims[4] = {(uint64_t)d, (uint64_t)n_k, (uint64_t)batch * kv_heads, (uint64_t)2 * world};
   uint64_t kstr[3] = {(uint64_t)d * 2, (uint64_t)n_k * d * 2, (uint64_t)batch * kv_heads * n_k * d * 2};
   uint32_t kbox[4] = {64, 128, 1, 1};
-  CUtensorMap map_kv = rab::make_tmap_bf16(kv_buf.data_ptr(), 4, kdims, kstr, kbox, rab::TmapSwizzle::B128);
+  const uint8_t* kv_base = reinterpret_cast<const uint8_t*>(kv_buf.data_ptr()) -
+                           (hop_mode ? (size_t)slot_owner * kstr[2] * 2 : 0);  // see attn_fwd_impl
+  CUtensorMap map_kv = rab::make_tmap_bf16(kv_base, 4, kdims, kstr, kbox, rab::TmapSwizzle::B128);
   // dQ accumulator: 2-D (d, b*h*n_pad) fp32, box 32 columns x 32 rows, no swizzle (rows written lane-contiguous)
   uint64_t adims[2] = {(uint64_t)d, (uint64_t)batch * heads * n_pad};
   uint64_t astr[1] = {(uint64_t)d * 4};
@@ -640,7 +715,10 @@ TORCH_LIBRARY(rab, m) {
   m.def("attn_bwd_ring(Tensor qdo, Tensor kv_buf, Tensor stat, Tensor(a!) dq_acc, Tensor? ready, int ready_target, "
         "Tensor? kmask_bits, int batch, int heads, int kv_heads, int rank, bool causal, int window, float scale, float "
         "softclamp, int pos_stride, int seg_len, int[] base0, int[] base1, int q_pos_offset, int[] hop_owner, int[] "
-        "dkv_acc_ptrs, int nk_pad) -> (Tensor, Tensor)");
+        "dkv_acc_ptrs, int nk_pad, int world_size=0, int slot_owner=-1) -> (Tensor, Tensor)");
+  m.def("attn_fwd_hop(Tensor q, Tensor kv_slot, int owner, int world, Tensor(a!) carry_o, Tensor(b!) carry_ml, bool "
+        "carry_in, bool carry_out, Tensor? kmask_bits, int kv_heads, int rank, bool causal, int window, float scale, "
+        "float softclamp, int pos_stride, int seg_len, int[] base0, int[] base1, int q_pos_offset) -> (Tensor, Tensor)");
   m.def("acc_convert(Tensor acc, Tensor(a!) out, float scale) -> ()");
   m.def("set_fetch_timing(Tensor? times) -> ()");
   m.def("device_barrier(int[] pad_ptrs, int rank, int epoch) -> ()");
@@ -654,6 +732,7 @@ TORCH_LIBRARY(rab, m) {
 TORCH_LIBRARY_IMPL(rab, CUDA, m) {
   m.impl("umma_probe", &umma_probe);
   m.impl("attn_fwd", &attn_fwd);
+  m.impl("attn_fwd_hop", &attn_fwd_hop);
   m.impl("pack_kv", &pack_kv);
   m.impl("rotary", &rotary);
   m.impl("tree_decode", &tree_decode);

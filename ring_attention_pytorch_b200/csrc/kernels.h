@@ -72,6 +72,12 @@ struct AttnFwdParams {
   unsigned long long slot_bytes;      // bytes of one owner slot (K and V)
   uint32_t* ready;                    // [world] arrival counters, zero before launch
   unsigned long long* fetch_times;    // optional [gridDim][2] globaltimer ns: first / last activity of each CTA's fetcher
+  // hop-at-a-time mode (memory = "ring"): one launch per ring hop, the online-softmax state travels between launches
+  float* carry_o;    // fp32 [b, n_q, h, d] un-normalised O (in / out), null = single-launch mode
+  float* carry_ml;   // fp32 [2][b*h][n_q]: running maximum (scaled log2 domain) and running sum
+  int carry_in;      // 1: initialise O / m / l of every item from the carry buffers
+  int carry_out;     // 1: store the un-normalised state instead of the final O / lse
+  int all_ready;     // 1: every slot this launch reads is already complete (no in-kernel fetch, no ready flags)
 };
 
 template <int D>

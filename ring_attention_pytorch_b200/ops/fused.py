@@ -58,6 +58,44 @@ def fused_attn_fwd(
         float(softclamp), pm.stride, pm.seg_len, pm.base0, pm.base1, int(q_pos_offset), list(hop_owner))
 
 
+def fused_attn_fwd_hop(
+    q: torch.Tensor,
+    kv_slot: torch.Tensor,
+    owner: int,
+    world: int,
+    carry_o: torch.Tensor,
+    carry_ml: torch.Tensor,
+    kmask_bits: Optional[torch.Tensor],
+    *,
+    carry_in: bool,
+    carry_out: bool,
+    kv_heads: int,
+    rank: int,
+    pm: PositionMap,
+    causal: bool,
+    window: Optional[int],
+    scale: float,
+    softclamp: float = 0.0,
+    q_pos_offset: int = 0,
+):
+    """ONE ring hop of the forward (``memory="ring"``): ``q`` against owner ``owner``'s K/V slot ``[2, b*hk, n_k, d]``.
+
+    The online-softmax state travels between the per-hop launches in ``carry_o`` (fp32 ``[b, n_q, h, d]``, the
+    un-normalised O) and ``carry_ml`` (fp32 ``[2, b*h, n_q]``: running maximum / sum); the launch with
+    ``carry_out=False`` returns the final (o, lse).  The reference carries (o, m, lse) between its per-hop Triton
+    launches the same way (ring_flash_attention_cuda.py:143-173)."""
+    return _ext.ops().attn_fwd_hop(
+        q, kv_slot[None], int(owner), int(world), carry_o, carry_ml, bool(carry_in), bool(carry_out), kmask_bits,
+        kv_heads, rank, bool(causal), int(window or 0), float(scale), float(softclamp), pm.stride, pm.seg_len, pm.base0,
+        pm.base1, int(q_pos_offset))
+
+
+def alloc_fwd_carry(q: torch.Tensor):
+    b, n_q, h, d = q.shape
+    return (torch.empty(b, n_q, h, d, dtype=torch.float32, device=q.device),
+            torch.empty(2, b * h, n_q, dtype=torch.float32, device=q.device))
+
+
 def emulate_ring_forward(
     qs: Sequence[torch.Tensor],
     ks: Sequence[torch.Tensor],
@@ -69,10 +107,12 @@ def emulate_ring_forward(
     softclamp: float = 0.0,
     key_masks: Optional[Sequence[torch.Tensor]] = None,
     scale: Optional[float] = None,
+    hopwise: bool = False,
 ):
     """Run the fused forward for every rank of a W-rank ring on the current device.
 
     qs/ks/vs: per-rank shards ``[b, n, h, d]`` / ``[b, n, hk, d]``.  Returns (outs, lses) lists.
+    ``hopwise``: one launch per hop with carried softmax state (the ``memory="ring"`` schedule).
     """
     ops = _ext.ops()
     world = len(qs)
@@ -89,6 +129,18 @@ def emulate_ring_forward(
     if key_masks is not None:
         kbits = pack_key_mask_bits(torch.stack(list(key_masks), 0))
     outs, lses = [], []
+    if hopwise:
+        for r in range(world):
+            q = qs[r].contiguous()
+            carry_o, carry_ml = alloc_fwd_carry(q)
+            hops = ring_hop_owners(pm, r, causal, window)
+            for s_, owner in enumerate(hops):
+                o, lse = fused_attn_fwd_hop(q, bufs[owner][owner], owner, world, carry_o, carry_ml, kbits,
+                                            carry_in=s_ > 0, carry_out=s_ + 1 < len(hops), kv_heads=hk, rank=r, pm=pm,
+                                            causal=causal, window=window, scale=scale, softclamp=softclamp)
+            outs.append(o)
+            lses.append(lse)
+        return outs, lses
     for r in range(world):
         ready = torch.zeros(world, dtype=torch.int32, device=dev)
         peers = [bufs[o][o].data_ptr() for o in range(world)]  # owner o's own slot
@@ -168,8 +220,13 @@ def fused_attn_bwd_ring(
     ready: Optional[torch.Tensor] = None,
     ready_target: int = 0,
     hop_owner: Optional[List[int]] = None,
+    world: int = 0,
+    slot_owner: int = -1,
 ):
     """The one-kernel (5-GEMM) backward, head dim 128 (``csrc/attn_bwd_fused_sm100.cu``).
+
+    ``slot_owner >= 0`` (``memory="ring"``): ``kv_buf`` is ONE owner's slot ``[1, 2, b*hk, n_k, d]`` of a ``world``
+    rank ring and the launch covers that hop only; ``dq_acc`` and the dK/dV accumulators add up across the launches.
 
     ``qdo`` [2, b*h, n_q, d] / ``stat`` [2, b*h, n_pad] are this rank's ``bwd_prep`` output, ``kv_buf`` the K/V gather.
     dQ (unscaled) is added into ``dq_acc`` (fp32 [b*h, n_pad, d], allocated zeroed when not given).  Without
@@ -185,7 +242,7 @@ def fused_attn_bwd_ring(
     dk, dv = ops.attn_bwd_ring(qdo, kv_buf, stat, dq_acc, ready, int(ready_target), kmask_bits, batch, heads, kv_heads,
                                rank, bool(causal), int(window or 0), float(scale), float(softclamp), pm.stride,
                                pm.seg_len, pm.base0, pm.base1, int(q_pos_offset), list(hop_owner),
-                               list(dkv_acc_ptrs), int(nk_pad))
+                               list(dkv_acc_ptrs), int(nk_pad), int(world), int(slot_owner))
     return dq_acc, dk, dv
 
 
@@ -198,8 +255,10 @@ def emulate_ring_backward(
     key_masks=None,
     scale: Optional[float] = None,
     fused: Optional[bool] = None,
+    hopwise: bool = False,
 ):
     """Backward of :func:`emulate_ring_forward` for every emulated rank on the current device.
+    ``hopwise`` (fused only): one launch per hop against a single K/V slot (the ``memory="ring"`` schedule).
 
     ``fused`` (default: head dim 128) selects the one-kernel backward: every emulated rank adds its dK / dV tiles into
     the owners' fp32 accumulators, exactly what the ranks of a real ring do over NVLink."""
@@ -230,9 +289,17 @@ def emulate_ring_backward(
         ptrs = [a.data_ptr() for a in accs]
         dqs, direct = [], []
         for r in range(world):
-            dq_acc, dk, dv = fused_attn_bwd_ring(qdo_all[r], stat_all[r], kv_all, kbits, batch=b, heads=h, kv_heads=hk,
-                                                 rank=r, pm=pm, causal=causal, window=window, scale=scale,
-                                                 softclamp=softclamp, dkv_acc_ptrs=ptrs, nk_pad=nk_pad)
+            if hopwise and ring:
+                dq_acc = None
+                for owner in ring_hop_owners(pm, r, causal, window):
+                    dq_acc, dk, dv = fused_attn_bwd_ring(
+                        qdo_all[r], stat_all[r], kv_all[owner:owner + 1], kbits, batch=b, heads=h, kv_heads=hk, rank=r,
+                        pm=pm, causal=causal, window=window, scale=scale, softclamp=softclamp, dq_acc=dq_acc,
+                        dkv_acc_ptrs=ptrs, nk_pad=nk_pad, hop_owner=[owner], world=world, slot_owner=owner)
+            else:
+                dq_acc, dk, dv = fused_attn_bwd_ring(qdo_all[r], stat_all[r], kv_all, kbits, batch=b, heads=h,
+                                                     kv_heads=hk, rank=r, pm=pm, causal=causal, window=window,
+                                                     scale=scale, softclamp=softclamp, dkv_acc_ptrs=ptrs, nk_pad=nk_pad)
             dqs.append(dq_acc)
             direct.append((dk, dv))
         for r in range(world):

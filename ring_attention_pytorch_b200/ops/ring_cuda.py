@@ -34,11 +34,13 @@ from torch.autograd import Function
 
 from ring_attention_pytorch_b200.ops import _ext
 from ring_attention_pytorch_b200.ops.fused import (
+    alloc_fwd_carry,
     alloc_kv_buffer,
     alloc_qdo_buffer,
     alloc_stat_buffer,
     fused_attn_bwd_ring,
     fused_attn_fwd,
+    fused_attn_fwd_hop,
     pack_key_mask_bits,
     pad128,
 )
@@ -54,7 +56,13 @@ LAUNCHES = {"count": 0}
 # backward="fused"     : head dim 128 runs the whole backward in ONE KV-stationary kernel (5 GEMMs; dQ through fp32 TMA
 #                        reductions, dK/dV added into the owner's accumulators over NVLink).
 # backward="two_kernel": the dQ + dK/dV kernel pair (7 GEMMs, no atomics, deterministic); head dim 64 always uses it.
-CONFIG = {"backward": "fused"}
+# memory="gather"      : one forward launch per rank; its fetcher warps pull all W-1 peer slots into a W-slot gather
+#                        buffer (transient, shared by all layers).  Fastest; workspace O(n) per rank.
+# memory="ring"        : one launch per ring hop against a 2-slot window that the copy engines fill one hop ahead; the
+#                        online-softmax state (forward) and the fp32 accumulators (backward, head dim 128) carry over
+#                        between the launches.  Workspace O(n / W) per rank like the reference's send/recv ring
+#                        (ring_flash_attention_cuda.py:128-178) — the mode for sequences the gather does not fit.
+CONFIG = {"backward": "fused", "memory": "gather"}
 
 
 def _count(n: int = 1) -> None:
@@ -83,6 +91,56 @@ def _ring_gather_workspace(ws, ring_size, b, hk, n_k, d_pad, dt):
     gather = local[:ring_size * slot_bytes].view(dt).view(ring_size, 2, b * hk, n_k, d_pad)
     own_slot_ptrs = [bases[o] + o * slot_bytes for o in range(ring_size)]
     return gather, own_slot_ptrs, slot_bytes
+
+
+def _own_slot_workspace(ws, b, hk, n_k, d_pad, dt):
+    """``memory="ring"``: this rank's own K/V slot ``[2, b*hk, n_k, d]`` in symmetric memory (double buffered across
+    calls) and every ring rank's address of ITS slot."""
+    slot_bytes = 2 * b * hk * n_k * d_pad * 2
+    local, bases = ws.staging("kv_own", slot_bytes)
+    return local[:slot_bytes].view(dt).view(2, b * hk, n_k, d_pad), bases, slot_bytes
+
+
+class _HopWindow:
+    """Two local K/V slots that the copy engines fill up to two hops ahead of the kernel that reads them.
+
+    Hop 0 reads this rank's own slot in place; hop s >= 1 reads ``win[(s - 1) % 2]``, pulled from its owner's symmetric slot
+    on the side stream.  Everything is stream ordered (events), nothing blocks the host.  Create it after the device
+    barrier that publishes the peers' slots."""
+
+    def __init__(self, ops, ws, own: Tensor, own_ptrs, slot_bytes: int, hops):
+        dev = own.device
+        self.ops, self.own, self.own_ptrs, self.slot_bytes, self.hops = ops, own, own_ptrs, slot_bytes, list(hops)
+        self.main, self.side = torch.cuda.current_stream(dev), ws.side_stream
+        self.win = torch.empty((min(2, max(len(self.hops) - 1, 0)),) + tuple(own.shape), dtype=own.dtype, device=dev)
+        self.copied = {}
+        start = torch.cuda.Event()
+        start.record(self.main)
+        self._prefetch(1, start)
+        self._prefetch(2, start)
+
+    def _prefetch(self, s: int, after) -> None:
+        if s >= len(self.hops):
+            return
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(after)
+            self.ops.peer_copy(self.win[(s - 1) % 2], self.own_ptrs[self.hops[s]], self.slot_bytes)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.copied[s] = ev
+
+    def slot(self, s: int) -> Tensor:
+        if s == 0:
+            return self.own
+        self.main.wait_event(self.copied.pop(s))
+        return self.win[(s - 1) % 2]
+
+    def launched(self, s: int) -> None:
+        """The kernel of hop ``s`` is enqueued: once it finishes its slot is free for hop s + 2."""
+        if s >= 1 and s + 2 < len(self.hops):
+            done = torch.cuda.Event()
+            done.record(self.main)
+            self._prefetch(s + 2, done)
 
 
 def _pack_slot(ops, k: Tensor, v: Tensor, slot: Tensor, angles: Optional[Tensor]) -> None:
@@ -168,8 +226,18 @@ class RingFlashAttentionCUDAFunction(Function):
         ready = torch.zeros(ring_size, dtype=torch.int32, device=dev)
         peers = [0] * ring_size
         kbits = None
+        hop_mode = use_ring and CONFIG["memory"] == "ring"
         with nvtx_range("rab.fwd.pack+barrier"):
-            if use_ring:
+            if hop_mode:
+                ws = get_workspace(ring_size, dev)
+                own, own_ptrs, slot_bytes = _own_slot_workspace(ws, b, hk, n_k, d_pad, dt)
+                _pack_slot(ops, kp, vp, own, ang if fused_k_rotary else None)
+                ws.barrier()  # every peer's own slot is complete
+                _count(2)
+                kv_gather = None
+                if exists(mask):
+                    kbits = pack_key_mask_bits(_gather_ring_masks(mask, ring_size))
+            elif use_ring:
                 ws = get_workspace(ring_size, dev)
                 kv_gather, own_slot_ptrs, _ = _ring_gather_workspace(ws, ring_size, b, hk, n_k, d_pad, dt)
                 _pack_slot(ops, kp, vp, kv_gather[rank], ang if fused_k_rotary else None)
@@ -187,9 +255,23 @@ class RingFlashAttentionCUDAFunction(Function):
 
         softclamp = float(softclamp_value) if softclamp_qk_sim else 0.0
         with nvtx_range("rab.fwd.kernel"):
-            o, lse = fused_attn_fwd(qp, kv_gather, peers, ready, kbits, kv_heads=hk, rank=rank, pm=pm, causal=causal,
-                                    window=max_lookback_seq_len, scale=scale, softclamp=softclamp, q_pos_offset=q_off)
-        _count()
+            if hop_mode:
+                hops = ring_hop_owners(pm, rank, causal, max_lookback_seq_len)
+                window_slots = _HopWindow(ops, ws, own, own_ptrs, slot_bytes, hops)
+                carry_o, carry_ml = alloc_fwd_carry(qp)
+                for s_, owner in enumerate(hops):
+                    o, lse = fused_attn_fwd_hop(qp, window_slots.slot(s_), owner, ring_size, carry_o, carry_ml, kbits,
+                                                carry_in=s_ > 0, carry_out=s_ + 1 < len(hops), kv_heads=hk, rank=rank,
+                                                pm=pm, causal=causal, window=max_lookback_seq_len, scale=scale,
+                                                softclamp=softclamp, q_pos_offset=q_off)
+                    window_slots.launched(s_)
+                    _count()
+                del carry_o, carry_ml
+            else:
+                o, lse = fused_attn_fwd(qp, kv_gather, peers, ready, kbits, kv_heads=hk, rank=rank, pm=pm,
+                                        causal=causal, window=max_lookback_seq_len, scale=scale, softclamp=softclamp,
+                                        q_pos_offset=q_off)
+                _count()
 
         ctx.cfg = (causal, max_lookback_seq_len, ring_size, rank, layout, softclamp, scale, q_off, use_ring, d, d_pad,
                    orig_dtype, hk, fused_k_rotary)
@@ -219,7 +301,14 @@ class RingFlashAttentionCUDAFunction(Function):
 
         ws = None
         kv_own_ptrs, kv_bytes = None, 0
-        if use_ring:  # rebuild the gather buffer around this rank's own slot (the forward's buffer is long reused)
+        hop_mode = use_ring and CONFIG["memory"] == "ring" and d_pad == 128 and CONFIG["backward"] == "fused"
+        if hop_mode:
+            ws = get_workspace(ring_size, dev)
+            own, kv_own_ptrs, kv_bytes = _own_slot_workspace(ws, b, hk, n_k, d_pad, dt)
+            _pack_slot(ops, kp, vp, own, ang if fused_k_rotary else None)
+            _count()
+            kv_gather = None
+        elif use_ring:  # rebuild the gather buffer around this rank's own slot (the forward's buffer is long reused)
             ws = get_workspace(ring_size, dev)
             kv_gather, kv_own_ptrs, kv_bytes = _ring_gather_workspace(ws, ring_size, b, hk, n_k, d_pad, dt)
             _pack_slot(ops, kp, vp, kv_gather[rank], ang if fused_k_rotary else None)
@@ -263,20 +352,34 @@ class RingFlashAttentionCUDAFunction(Function):
                     acc_ptrs = region.peer_ptrs
                     ws.barrier()  # every peer's accumulators are zero and its own K/V slot is complete
                     _count(2)
-                    ready, side_done = pull_kv_slots()
-                    ready_target = 1
+                    if not hop_mode:
+                        ready, side_done = pull_kv_slots()
+                        ready_target = 1
             with nvtx_range("rab.bwd.kernel"):
-                _, dk, dv = fused_attn_bwd_ring(qdo[0], stat[0], kv_gather, kbits, batch=b, heads=h, kv_heads=hk,
-                                                rank=rank, pm=pm, causal=causal, window=window, scale=scale,
-                                                softclamp=softclamp, q_pos_offset=q_off, dq_acc=dq_acc,
-                                                dkv_acc_ptrs=acc_ptrs, nk_pad=nk_pad, ready=ready,
-                                                ready_target=ready_target, hop_owner=hop_owner)
+                if hop_mode:  # one launch per hop against the 2-slot window; dq_acc / the owners' dK, dV accumulate
+                    window_slots = _HopWindow(ops, ws, own, kv_own_ptrs, kv_bytes, hop_owner)
+                    for s_, owner in enumerate(hop_owner):
+                        fused_attn_bwd_ring(qdo[0], stat[0], window_slots.slot(s_)[None], kbits, batch=b, heads=h,
+                                            kv_heads=hk, rank=rank, pm=pm, causal=causal, window=window, scale=scale,
+                                            softclamp=softclamp, q_pos_offset=q_off, dq_acc=dq_acc,
+                                            dkv_acc_ptrs=acc_ptrs, nk_pad=nk_pad, hop_owner=[owner], world=ring_size,
+                                            slot_owner=owner)
+                        window_slots.launched(s_)
+                        _count()
+                    _count(-1)
+                else:
+                    _, dk, dv = fused_attn_bwd_ring(qdo[0], stat[0], kv_gather, kbits, batch=b, heads=h, kv_heads=hk,
+                                                    rank=rank, pm=pm, causal=causal, window=window, scale=scale,
+                                                    softclamp=softclamp, q_pos_offset=q_off, dq_acc=dq_acc,
+                                                    dkv_acc_ptrs=acc_ptrs, nk_pad=nk_pad, ready=ready,
+                                                    ready_target=ready_target, hop_owner=hop_owner)
                 dq = torch.empty(b, n_q, h, d_pad, dtype=dt, device=dev)
                 ops.acc_convert(dq_acc, dq, scale)
                 _count(2)
             if use_ring:
                 with nvtx_range("rab.bwd.barrier+convert"):
-                    torch.cuda.current_stream(dev).wait_event(side_done)
+                    if side_done is not None:
+                        torch.cuda.current_stream(dev).wait_event(side_done)
                     ws.barrier()  # every rank's kernel has finished adding into this rank's accumulators
                     dk = torch.empty(b, n_k, hk, d_pad, dtype=dt, device=dev)
                     dv = torch.empty_like(dk)

@@ -81,6 +81,26 @@ def test_fused_backward(name):
     assert res["ok"], res
 
 
+# memory="ring": one launch per hop against a single K/V slot, softmax state / fp32 accumulators carried between launches
+HOP_CASES = {k: dict(v, hopwise=True) for k, v in FWD_CASES.items() if k.startswith("ring")}
+HOP_CASES["ring4_d64_striped_causal"] = dict(world=4, n=300, h=4, hk=2, d=64, layout="striped", causal=True, hopwise=True)
+HOP_CASES["ring8_plain_window_sparse"] = dict(world=8, n=256, h=2, causal=True, window=300, hopwise=True)
+HOP_CASES["ring4_softclamp_fp16"] = dict(world=4, n=384, h=2, layout="zigzag", causal=True, softclamp=20.0, dtype="fp16",
+                                         hopwise=True)
+
+
+@pytest.mark.parametrize("name", list(HOP_CASES))
+def test_hopwise_forward(name):
+    res = _cases().case_fwd(**HOP_CASES[name])
+    assert res["ok"], res
+
+
+@pytest.mark.parametrize("name", [k for k, v in HOP_CASES.items() if v.get("d", 128) == 128])
+def test_hopwise_backward(name):
+    res = _cases().case_bwd(**HOP_CASES[name])
+    assert res["ok"], res
+
+
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("d", [32, 64, 128])
 def test_autograd_op_matches_oracle(causal, d):
@@ -149,12 +169,13 @@ def test_graft_smoke():
 # ------------------------------------------------------------------------------------------------
 # real multi-GPU ring (NVLink, symmetric memory) – needs >= 2 devices
 # ------------------------------------------------------------------------------------------------
-def _ring_worker(rank, world, layout, causal, hk, kmask=False, backward="fused"):
+def _ring_worker(rank, world, layout, causal, hk, kmask=False, backward="fused", memory="gather"):
     import torch.distributed as dist
 
     from ring_attention_pytorch_b200.ops import ring_cuda
 
     ring_cuda.CONFIG["backward"] = backward
+    ring_cuda.CONFIG["memory"] = memory
 
     from ring_attention_pytorch_b200.ops.oracle import attention_with_positions
     from ring_attention_pytorch_b200.ops.ring_cuda import ring_flash_attn_cuda
@@ -194,20 +215,24 @@ def _ring_worker(rank, world, layout, causal, hk, kmask=False, backward="fused")
     dist.barrier()
 
 
-@pytest.mark.parametrize("layout,causal,hk,kmask,backward", [("plain", False, 4, False, "fused"),
-                                                             ("striped", True, 2, False, "fused"),
-                                                             ("zigzag", True, 4, False, "fused"),
-                                                             ("plain", False, 2, True, "fused"),
-                                                             ("striped", True, 2, False, "two_kernel"),
-                                                             ("plain", False, 4, True, "two_kernel")])
-def test_real_ring_two_gpus(layout, causal, hk, kmask, backward):
+@pytest.mark.parametrize("layout,causal,hk,kmask,backward,memory", [("plain", False, 4, False, "fused", "gather"),
+                                                                    ("striped", True, 2, False, "fused", "gather"),
+                                                                    ("zigzag", True, 4, False, "fused", "gather"),
+                                                                    ("plain", False, 2, True, "fused", "gather"),
+                                                                    ("striped", True, 2, False, "two_kernel", "gather"),
+                                                                    ("plain", False, 4, True, "two_kernel", "gather"),
+                                                                    ("striped", True, 2, False, "fused", "ring"),
+                                                                    ("plain", True, 4, False, "fused", "ring"),
+                                                                    ("zigzag", True, 4, True, "fused", "ring"),
+                                                                    ("plain", False, 2, True, "two_kernel", "ring")])
+def test_real_ring_two_gpus(layout, causal, hk, kmask, backward, memory):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     from dist_utils import run_distributed
 
     world = min(torch.cuda.device_count(), 8)
     world = 2 if world < 4 else 4
-    run_distributed(_ring_worker, world, layout, causal, hk, kmask, backward, backend="nccl")
+    run_distributed(_ring_worker, world, layout, causal, hk, kmask, backward, memory, backend="nccl")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -465,12 +490,14 @@ def test_tcgen05_issue_rate_matches_hardware_floor():
 # ------------------------------------------------------------------------------------------------
 # real rings at a size where a localized bug would show: sampled rows against the chunked fp32 oracle
 # ------------------------------------------------------------------------------------------------
-def _big_ring_worker(rank, world, layout, n, h, hk, ring_size):
+def _big_ring_worker(rank, world, layout, n, h, hk, ring_size, memory="gather"):
     import torch.distributed as dist
 
+    from ring_attention_pytorch_b200.ops import ring_cuda
     from ring_attention_pytorch_b200.ops.ring_cuda import ring_flash_attn_cuda
     from ring_attention_pytorch_b200.utils.check import sampled_check
 
+    ring_cuda.CONFIG["memory"] = memory
     ring_size = ring_size or world
     torch.manual_seed(100 + rank)
     dev = torch.device("cuda", rank)
@@ -484,6 +511,13 @@ def _big_ring_worker(rank, world, layout, n, h, hk, ring_size):
         res = sampled_check(q.detach(), k.detach(), v.detach(), g, out.detach(), dq, dk, dv, causal=True, layout=layout,
                             world=world, rank=rank, head_index=h - 1, samples=48, chunk=1024)
         assert res["ok"], res
+        if memory == "ring":
+            # the workspace is O(n / W): this rank's own K/V slot (double buffered), never a W-slot gather
+            from ring_attention_pytorch_b200.parallel.symm import get_workspace
+
+            regions = get_workspace(ring_size, dev).regions
+            slot = 2 * n * hk * 128 * 2
+            assert "kv_gather" not in regions and regions["kv_own"].nbytes <= 2 * slot + 1024, list(regions)
     else:
         # ring sets: every set is an independent ring; check inside the set through a sub-group gather
         sets = world // ring_size
@@ -522,6 +556,19 @@ def test_real_ring_all_gpus_sampled_oracle(layout, hk):
 
     world = 8 if world >= 8 else (4 if world >= 4 else 2)
     run_distributed(_big_ring_worker, world, layout, 8192, 8, hk, None, backend="nccl", timeout=600.0)
+
+
+@pytest.mark.parametrize("layout,hk", [("striped", 2), ("zigzag", 8)])
+def test_real_ring_hop_window_memory_mode(layout, hk):
+    """``CONFIG["memory"] = "ring"``: per-hop launches against a 2-slot window (copy engines one hop ahead), carried
+    softmax state and accumulators; same sampled-oracle check, and the symmetric workspace stays O(n / W)."""
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from dist_utils import run_distributed
+
+    world = 8 if world >= 8 else (4 if world >= 4 else 2)
+    run_distributed(_big_ring_worker, world, layout, 8192, 8, hk, None, "ring", backend="nccl", timeout=600.0)
 
 
 def test_ring_sets_two_by_four():

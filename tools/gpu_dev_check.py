@@ -98,7 +98,7 @@ def _ref_ring(qs, ks, vs, layout, causal, window, softclamp, key_masks):
 
 
 def case_fwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=False, window=None, softclamp=0.0,
-             kmask=False, dtype="bf16", seed=0):
+             kmask=False, dtype="bf16", seed=0, hopwise=False):
     import torch
     from ring_attention_pytorch_b200.ops.fused import emulate_ring_forward
 
@@ -112,7 +112,7 @@ def case_fwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=Fa
     if kmask:
         kms = [torch.rand(b, n, device="cuda") > 0.3 for _ in range(world)]
     outs, lses = emulate_ring_forward(qs, ks, vs, layout=layout, causal=causal, window=window, softclamp=softclamp,
-                                      key_masks=kms)
+                                      key_masks=kms, hopwise=hopwise)
     torch.cuda.synchronize()
     routs, rlses = _ref_ring(qs, ks, vs, layout, causal, window, softclamp, kms)
     err = max((o.float() - r).abs().max().item() for o, r in zip(outs, routs))
@@ -123,7 +123,7 @@ def case_fwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=Fa
 
 
 def case_bwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=False, window=None, softclamp=0.0,
-             kmask=False, dtype="bf16", seed=0, fused=None):
+             kmask=False, dtype="bf16", seed=0, fused=None, hopwise=False):
     import torch
     from ring_attention_pytorch_b200.ops.fused import emulate_ring_backward, emulate_ring_forward
     from ring_attention_pytorch_b200.ops.oracle import attention_with_positions
@@ -140,9 +140,9 @@ def case_bwd(world=1, b=1, n=256, h=2, hk=None, d=128, layout="plain", causal=Fa
     if kmask:
         kms = [torch.rand(b, n, device="cuda") > 0.3 for _ in range(world)]
     outs, lses = emulate_ring_forward(qs, ks, vs, layout=layout, causal=causal, window=window, softclamp=softclamp,
-                                      key_masks=kms)
+                                      key_masks=kms, hopwise=hopwise)
     grads = emulate_ring_backward(qs, ks, vs, outs, lses, dos, layout=layout, causal=causal, window=window,
-                                  softclamp=softclamp, key_masks=kms, fused=fused)
+                                  softclamp=softclamp, key_masks=kms, fused=fused, hopwise=hopwise)
     torch.cuda.synchronize()
     # fp32 oracle through autograd
     pm = make_position_map(layout, world, n)
@@ -362,6 +362,93 @@ def case_perf_decode(batch=256, h=32, hk=8, n=8192, d=128, fp8=False, iters=20, 
             "tensor_core": tensor_core, "launches_per_step": 1, "ok": err < 3e-2}
 
 
+def case_perf_hop(world=4, n=16384, h=8, hk=None, d=128, layout="striped", causal=True, iters=3):
+    """Cost of the hop-at-a-time schedule (memory="ring") against the single-launch schedule for one emulated rank:
+    same K/V slots (already local: no transfer in either arm), forward and one-kernel backward."""
+    import torch
+    from ring_attention_pytorch_b200.ops import _ext
+    from ring_attention_pytorch_b200.ops.fused import (alloc_fwd_carry, alloc_kv_buffer, alloc_qdo_buffer,
+                                                       alloc_stat_buffer, fused_attn_bwd_ring, fused_attn_fwd,
+                                                       fused_attn_fwd_hop, pad128)
+    from ring_attention_pytorch_b200.parallel.layout import make_position_map, ring_hop_owners
+
+    ops = _ext.ops()
+    hk = hk or h
+    dt = torch.bfloat16
+    b, rank = 1, world - 1
+    q = torch.randn(b, n, h, d, device="cuda", dtype=dt)
+    do = torch.randn(b, n, h, d, device="cuda", dtype=dt)
+    buf = alloc_kv_buffer(world, b, hk, n, d, dt, "cuda")
+    for o_ in range(world):
+        ops.pack_kv(torch.randn(b, n, hk, d, device="cuda", dtype=dt), torch.randn(b, n, hk, d, device="cuda", dtype=dt),
+                    buf[o_])
+    pm = make_position_map(layout, world, n)
+    hops = ring_hop_owners(pm, rank, causal, None)
+    ready = torch.zeros(world, dtype=torch.int32, device="cuda")
+    peers = [0] * world  # every slot is local: the fetchers copy slot -> slot (same bytes a real ring pulls)
+    kw = dict(kv_heads=hk, rank=rank, pm=pm, causal=causal, window=None, scale=d ** -0.5)
+    carry_o, carry_ml = alloc_fwd_carry(q)
+    accs = [torch.zeros(2, b * hk, pad128(n), d, dtype=torch.float32, device="cuda") for _ in range(world)]
+    ptrs = [a.data_ptr() for a in accs]
+    state = {}
+
+    def fwd_single():
+        state["o"], state["lse"] = fused_attn_fwd(q, buf, [buf[o_].data_ptr() if o_ != rank else 0 for o_ in range(world)],
+                                                  ready, None, **kw)
+
+    def fwd_hop():
+        for s_, owner in enumerate(hops):
+            state["o"], state["lse"] = fused_attn_fwd_hop(q, buf[owner], owner, world, carry_o, carry_ml, None,
+                                                          carry_in=s_ > 0, carry_out=s_ + 1 < len(hops), **kw)
+
+    def prep():
+        qdo = alloc_qdo_buffer(1, b, h, n, d, dt, "cuda")
+        stat = alloc_stat_buffer(1, b, h, n, "cuda")
+        ops.bwd_prep(q, state["o"], do, state["lse"], qdo, stat, 0)
+        return qdo, stat
+
+    def bwd_single():
+        fused_attn_bwd_ring(state["qdo"][0], state["stat"][0], buf, None, batch=b, heads=h, dq_acc=state["dq"],
+                            dkv_acc_ptrs=ptrs, nk_pad=pad128(n), **kw)
+
+    def bwd_hop():
+        for owner in hops:
+            fused_attn_bwd_ring(state["qdo"][0], state["stat"][0], buf[owner:owner + 1], None, batch=b, heads=h,
+                                dq_acc=state["dq"], dkv_acc_ptrs=ptrs, nk_pad=pad128(n), hop_owner=[owner], world=world,
+                                slot_owner=owner, **kw)
+
+    def timeit(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    res = {"hops": len(hops)}
+    res["fwd_single_ms"] = timeit(fwd_single)
+    o_ref = state["o"].clone()
+    res["fwd_hop_ms"] = timeit(fwd_hop)
+    res["fwd_max_diff"] = (state["o"].float() - o_ref.float()).abs().max().item()
+    state["qdo"], state["stat"] = prep()
+    state["dq"] = torch.zeros(b * h, state["stat"].shape[-1], d, dtype=torch.float32, device="cuda")
+    res["bwd_single_ms"] = timeit(bwd_single)
+    res["bwd_hop_ms"] = timeit(bwd_hop)
+    flops = 4.0 * b * h * n * (n * world) * d * (0.5 if causal else 1.0)
+    res["fwd_single_tflops"] = flops / res["fwd_single_ms"] / 1e9
+    res["fwd_hop_tflops"] = flops / res["fwd_hop_ms"] / 1e9
+    res["bwd_single_tflops"] = 2.5 * flops / res["bwd_single_ms"] / 1e9
+    res["bwd_hop_tflops"] = 2.5 * flops / res["bwd_hop_ms"] / 1e9
+    res["ok"] = res["fwd_max_diff"] < 2e-2
+    return res
+
+
 def case_perf(n=16384, h=16, d=128, causal=True, iters=5, b=1, hk=None):
     import torch
     from ring_attention_pytorch_b200.ops import _ext
@@ -496,6 +583,8 @@ CASES = {
     "perfdec_cudacore_bf16": lambda: case_perf_decode(tensor_core=False),
     "perfdec_cudacore_fp8": lambda: case_perf_decode(fp8=True, tensor_core=False),
     "perfdec_g16_bf16": lambda: case_perf_decode(batch=64, h=64, hk=4, n=16384),
+    "perfhop_w4_striped_16k": lambda: case_perf_hop(),
+    "perfhop_w8_striped_8k_h16": lambda: case_perf_hop(world=8, n=8192, h=16),
     "perf_causal_16k": lambda: case_perf(),
     "perf_full_8k": lambda: case_perf(n=8192, causal=False),
     "perf_causal_64k_h8": lambda: case_perf(n=65536, h=8, iters=3),
@@ -513,6 +602,7 @@ GROUPS = {
     "perfbwd": [c for c in CASES if c.startswith("perfbwd")],
     "perfdec": [c for c in CASES if c.startswith("perfdec")],
     "perf": [c for c in CASES if c.startswith("perf_")],
+    "perfhop": [c for c in CASES if c.startswith("perfhop")],
 }
 
 
