@@ -223,7 +223,8 @@ def _ring_worker(rank, world, layout, causal, hk, kmask=False, backward="fused",
                                                                     ("plain", False, 4, True, "two_kernel", "gather"),
                                                                     ("striped", True, 2, False, "fused", "ring"),
                                                                     ("plain", True, 4, False, "fused", "ring"),
-                                                                    ("zigzag", True, 4, True, "fused", "ring"),
+                                                                    ("zigzag", True, 4, False, "fused", "ring"),
+                                                                    ("plain", False, 2, True, "fused", "ring"),
                                                                     ("plain", False, 2, True, "two_kernel", "ring")])
 def test_real_ring_two_gpus(layout, causal, hk, kmask, backward, memory):
     if torch.cuda.device_count() < 2:
