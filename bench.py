@@ -280,6 +280,7 @@ def main():
     def measure(S_: int, steps: int, warmup: int, with_e2e: bool, with_check: bool, sample_clocks: bool):
         """One configuration: device-timed loop (+ e2e loop, + sampled-row check).  Returns a dict (rank 0 prints)."""
         n_ = S_ // world
+        torch.cuda.reset_peak_memory_stats(dev)
         torch.manual_seed(1234 + rank)
         q = torch.randn(B, n_, H, D, device=dev, dtype=dt, requires_grad=True)
         k = torch.randn(B, n_, HK, D, device=dev, dtype=dt, requires_grad=True)
@@ -315,7 +316,7 @@ def main():
             steps = max(2, min(steps, int(args.ref_budget_s / max(per, 1e-6))))
 
         fetch_times = None
-        if args.impl == "ours" and world > 1:
+        if args.impl == "ours" and world > 1 and args.memory == "gather":
             fetch_times = torch.zeros(256, 2, dtype=torch.int64, device=dev)
             torch.ops.rab.set_fetch_timing(fetch_times)
             step()
@@ -349,6 +350,16 @@ def main():
             "gpu_launches": n_launch if args.impl == "ours" else 0,
             "clocks": clocks,
         }
+        if args.impl == "ours":
+            # device memory: caching-allocator peak + the symmetric (cudaMalloc / IPC) workspace of the ring
+            symm = 0
+            if world > 1:
+                from ring_attention_pytorch_b200.parallel.symm import get_workspace
+
+                symm = sum(r.nbytes for r in get_workspace(world, dev).regions.values())
+            row["memory_gb"] = {"allocator_peak": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                                "symmetric_workspace": symm / 2 ** 30,
+                                "inputs_q_k_v_w": (2 * B * n_ * H * D + 2 * B * n_ * HK * D) * 2 / 2 ** 30}
         # roofline: the slower of FLOPs at the measured sustained GEMM rate and the bytes that must cross NVLink
         kv_bytes_fwd = (world - 1) * 2 * B * n_ * HK * D * 2  # K/V slots a rank pulls in the forward
         link_bytes = kv_bytes_fwd * (1 if args.fwd_only else 2) + (0 if args.fwd_only else (world - 1) * 2 * B * n_ * HK * D * 4)
@@ -530,6 +541,7 @@ def main():
             "roofline": main_row["roofline"],
             **({"ring_kv_gbps": main_row["ring_kv_gbps"]} if "ring_kv_gbps" in main_row else {}),
             **({"check": main_row["check"]} if "check" in main_row else {}),
+            **({"memory_gb": main_row["memory_gb"]} if "memory_gb" in main_row else {}),
             "rows": rows,
         }
         print(json.dumps(line))
