@@ -54,7 +54,7 @@ def parse_args():
                     help="reference arm only: cap the timed steps so that one timed loop stays inside this budget")
     ap.add_argument("--probe-device", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--fwd-only", action="store_true", help="diagnostic only (not a valid headline number)")
-    ap.add_argument("--memory", default="gather", choices=["gather", "ring"],
+    ap.add_argument("--memory", default="ring", choices=["gather", "ring"],
                     help="ring_cuda.CONFIG['memory']: 'ring' = per-hop launches against a 2-slot K/V window (O(n/W) workspace)")
     return ap.parse_args()
 
@@ -383,6 +383,30 @@ def main():
                                        "bytes_per_rank": kv_bytes_fwd,
                                        "how": "forward K/V bytes pulled per rank / window in which its 148 in-kernel "
                                               "fetchers were active (globaltimer), min over ranks"}
+
+        if args.impl == "ours" and world > 1 and args.memory == "ring":
+            # the 2-slot window is filled by the copy engines: time a standalone pull of the forward's K/V bytes
+            from ring_attention_pytorch_b200.ops.ring_cuda import _own_slot_workspace
+            from ring_attention_pytorch_b200.parallel.symm import get_workspace
+
+            ws = get_workspace(world, dev)
+            own, own_ptrs, slot_bytes = _own_slot_workspace(ws, B, HK, n_, D, dt)
+            dst = torch.empty_like(own)
+            ws.barrier()
+            sync()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for s_ in range(1, world):  # ring order: no two ranks read one source at the same time
+                torch.ops.rab.peer_copy(dst, own_ptrs[(rank - s_) % world], slot_bytes)
+            c1.record()
+            sync()
+            t = torch.tensor([kv_bytes_fwd / (c0.elapsed_time(c1) * 1e6)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            row["ring_kv_gbps"] = {"value": float(t.item()), "of_nvlink_770": float(t.item()) / peaks["nvlink_gbs"],
+                                   "bytes_per_rank": kv_bytes_fwd,
+                                   "how": "copy-engine pull of the forward's K/V slots from every peer (what fills the "
+                                          "2-slot window one hop ahead), standalone after the timed loop, min over ranks"}
+            del dst
 
         # ---------------- end-to-end: pinned host inputs -> device every step, loss read back ------------
         if with_e2e and not args.fwd_only:

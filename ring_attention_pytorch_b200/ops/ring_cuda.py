@@ -3,21 +3,35 @@
 Public surface mirrors reference ring_flash_attention_cuda.py:353-371 (``ring_flash_attn_cuda`` /
 ``ring_flash_attn_cuda_``) plus a ``layout`` argument ('plain' | 'striped' | 'zigzag').
 
-Forward, per rank (one stream, no host synchronisation, no NCCL on the hot path):
+Forward, per rank (no host synchronisation, no NCCL on the hot path), ``CONFIG["memory"]``:
 
-    pack_kv (K,V -> head-major) straight into this rank's slot of the SYMMETRIC gather workspace -> device barrier ->
-    ONE fused kernel: tcgen05 flash attention over every hop of the ring while its fetcher warps pull the other
-    ranks' K/V slots over NVLink (bulk TMA) into the local gather buffer
+``"ring"`` (default) — O(n / W) workspace, like the reference's send/recv ring (ring_flash_attention_cuda.py:128-178):
+
+    pack_kv (K,V -> head-major) into this rank's own SYMMETRIC slot -> device barrier -> one tcgen05 flash-attention
+    launch per ring hop; hop 0 reads the own slot in place, hop s reads a 2-slot window that the COPY ENGINES fill up
+    to two hops ahead over NVLink (side stream, events); the un-normalised O / running max / running sum travel between
+    the launches in fp32 buffers (in TMEM inside a launch)
+
+``"gather"`` — one launch per rank for the whole ring:
+
+    pack_kv straight into this rank's slot of a W-slot symmetric gather workspace -> device barrier -> ONE fused
+    kernel: flash attention over every hop while its fetcher warps pull the other ranks' K/V slots over NVLink
+    (bulk TMA) into the local gather buffer; O / max / sum never leave TMEM and registers
+
+Measured at the headline config (S=262144, h=32, fwd+bwd): 2 GPUs 1656 vs 1646 TFLOP/s, 8 GPUs 6369 vs 6174 TFLOP/s
+("ring" vs "gather"; the copy engines move the bytes without taking shared-memory bandwidth from the MMA pipeline),
+and S = 4 194 304 on 8 GPUs runs in "ring" (96 GB per GPU) where the W-slot gather alone would need 137 GB.
 
 Only q, k, v, o and the log-sum-exp are saved for the backward (O(n / W) activation memory per layer; the reference
-saves the same, ring_flash_attention_cuda.py:188-198).  The gather workspace is transient and shared by all layers.
+saves the same, ring_flash_attention_cuda.py:188-198).  The workspaces are transient and shared by all layers.
 
 Backward, head dim 128 (``CONFIG["backward"] = "fused"``):
 
-    bwd_prep (delta, lse -> log2, Q/dO head-major) -> pack_kv into the gather workspace, zero the fp32 accumulators
-    -> device barrier -> [copy engines re-pull the peers' K/V slots on a side stream and publish per-owner flags] ->
-    ONE kernel: 5 GEMMs per tile pair, dQ added into a local fp32 accumulator (TMA reduction), dK/dV tiles added into
-    their OWNER's fp32 accumulators over NVLink from the kernel's epilogue -> device barrier -> fp32 -> 16 bit
+    bwd_prep (delta, lse -> log2, Q/dO head-major) -> pack_kv into the own slot, zero the fp32 accumulators
+    -> device barrier -> the one-kernel backward (5 GEMMs per tile pair, dQ added into a local fp32 accumulator by TMA
+    reduction, dK/dV tiles added into their OWNER's fp32 accumulators over NVLink from the kernel's epilogue), launched
+    once per hop against the 2-slot window ("ring") or once over the gathered slots, which the copy engines re-pull
+    behind per-owner flags ("gather") -> device barrier -> fp32 -> 16 bit
 
 Head dim 64 (or ``CONFIG["backward"] = "two_kernel"``): dQ kernel + dK/dV kernel (7 GEMMs, no atomics, deterministic),
 the peers' Q / dO / statistics pulled by the copy engines while the dQ kernel runs.
@@ -56,13 +70,14 @@ LAUNCHES = {"count": 0}
 # backward="fused"     : head dim 128 runs the whole backward in ONE KV-stationary kernel (5 GEMMs; dQ through fp32 TMA
 #                        reductions, dK/dV added into the owner's accumulators over NVLink).
 # backward="two_kernel": the dQ + dK/dV kernel pair (7 GEMMs, no atomics, deterministic); head dim 64 always uses it.
+# memory="ring"        : one launch per ring hop against a 2-slot window that the copy engines fill ahead of the
+#                        kernels; the online-softmax state (forward) and the fp32 accumulators (backward, head dim 128)
+#                        carry over between the launches.  Workspace O(n / W) per rank.  Default: also the faster one at
+#                        2 and 8 GPUs (see the module docstring).
 # memory="gather"      : one forward launch per rank; its fetcher warps pull all W-1 peer slots into a W-slot gather
-#                        buffer (transient, shared by all layers).  Fastest; workspace O(n) per rank.
-# memory="ring"        : one launch per ring hop against a 2-slot window that the copy engines fill one hop ahead; the
-#                        online-softmax state (forward) and the fp32 accumulators (backward, head dim 128) carry over
-#                        between the launches.  Workspace O(n / W) per rank like the reference's send/recv ring
-#                        (ring_flash_attention_cuda.py:128-178) — the mode for sequences the gather does not fit.
-CONFIG = {"backward": "fused", "memory": "gather"}
+#                        buffer (transient, shared by all layers); workspace O(n) per rank.  The head-dim-64 / two-kernel
+#                        backward always gathers.
+CONFIG = {"backward": "fused", "memory": "ring"}
 
 
 def _count(n: int = 1) -> None:
