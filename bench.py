@@ -54,8 +54,9 @@ def parse_args():
                     help="reference arm only: cap the timed steps so that one timed loop stays inside this budget")
     ap.add_argument("--probe-device", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--fwd-only", action="store_true", help="diagnostic only (not a valid headline number)")
-    ap.add_argument("--memory", default="ring", choices=["gather", "ring"],
-                    help="ring_cuda.CONFIG['memory']: 'ring' = per-hop launches against a 2-slot K/V window (O(n/W) workspace)")
+    ap.add_argument("--memory", default="auto", choices=["auto", "gather", "ring"],
+                    help="ring_cuda.CONFIG['memory']: 'ring' = per-hop launches against a 2-slot K/V window (O(n/W) "
+                         "workspace); 'auto' picks it for K/V slots >= 128 MiB per rank (the headline config at any N)")
     return ap.parse_args()
 
 
@@ -316,7 +317,9 @@ def main():
             steps = max(2, min(steps, int(args.ref_budget_s / max(per, 1e-6))))
 
         fetch_times = None
-        if args.impl == "ours" and world > 1 and args.memory == "gather":
+        hop_window = args.impl == "ours" and world > 1 and (
+            args.memory == "ring" or (args.memory == "auto" and 2 * B * n_ * HK * D * 2 >= (128 << 20)))
+        if args.impl == "ours" and world > 1 and not hop_window:
             fetch_times = torch.zeros(256, 2, dtype=torch.int64, device=dev)
             torch.ops.rab.set_fetch_timing(fetch_times)
             step()
@@ -350,6 +353,7 @@ def main():
             "gpu_launches": n_launch if args.impl == "ours" else 0,
             "clocks": clocks,
         }
+        row["hop_window"] = bool(hop_window)
         if args.impl == "ours":
             # device memory: caching-allocator peak + the symmetric (cudaMalloc / IPC) workspace of the ring
             symm = 0
@@ -384,7 +388,7 @@ def main():
                                        "how": "forward K/V bytes pulled per rank / window in which its 148 in-kernel "
                                               "fetchers were active (globaltimer), min over ranks"}
 
-        if args.impl == "ours" and world > 1 and args.memory == "ring":
+        if hop_window:
             # the 2-slot window is filled by the copy engines: time a standalone pull of the forward's K/V bytes
             from ring_attention_pytorch_b200.ops.ring_cuda import _own_slot_workspace
             from ring_attention_pytorch_b200.parallel.symm import get_workspace
@@ -554,7 +558,7 @@ def main():
                 "flops": "fwd 4*b*h*S^2*d*0.5, bwd 2.5x fwd (algorithmic 5-GEMM count)",
                 "l2": "inputs larger than L2 (no flush needed)",
                 "fwd_only": bool(args.fwd_only),
-                "memory": args.memory,
+                "memory": args.memory + (" (hop window)" if main_row.get("hop_window") else ""),
                 **({"reference_env": ref_env} if ref_env else {}),
                 **({"steps_requested": args.steps} if main_row["steps"] != args.steps else {}),
             },

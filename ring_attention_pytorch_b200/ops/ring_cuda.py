@@ -5,14 +5,14 @@ Public surface mirrors reference ring_flash_attention_cuda.py:353-371 (``ring_fl
 
 Forward, per rank (no host synchronisation, no NCCL on the hot path), ``CONFIG["memory"]``:
 
-``"ring"`` (default) — O(n / W) workspace, like the reference's send/recv ring (ring_flash_attention_cuda.py:128-178):
+``"ring"`` (what the default ``"auto"`` picks for K/V slots >= 128 MiB per rank) — O(n / W) workspace, like the reference's send/recv ring (ring_flash_attention_cuda.py:128-178):
 
     pack_kv (K,V -> head-major) into this rank's own SYMMETRIC slot -> device barrier -> one tcgen05 flash-attention
     launch per ring hop; hop 0 reads the own slot in place, hop s reads a 2-slot window that the COPY ENGINES fill up
     to two hops ahead over NVLink (side stream, events); the un-normalised O / running max / running sum travel between
     the launches in fp32 buffers (in TMEM inside a launch)
 
-``"gather"`` — one launch per rank for the whole ring:
+``"gather"`` (``"auto"`` for short shards) — one launch per rank for the whole ring:
 
     pack_kv straight into this rank's slot of a W-slot symmetric gather workspace -> device barrier -> ONE fused
     kernel: flash attention over every hop while its fetcher warps pull the other ranks' K/V slots over NVLink
@@ -72,12 +72,23 @@ LAUNCHES = {"count": 0}
 # backward="two_kernel": the dQ + dK/dV kernel pair (7 GEMMs, no atomics, deterministic); head dim 64 always uses it.
 # memory="ring"        : one launch per ring hop against a 2-slot window that the copy engines fill ahead of the
 #                        kernels; the online-softmax state (forward) and the fp32 accumulators (backward, head dim 128)
-#                        carry over between the launches.  Workspace O(n / W) per rank.  Default: also the faster one at
-#                        2 and 8 GPUs (see the module docstring).
+#                        carry over between the launches.  Workspace O(n / W) per rank; faster than "gather" at the
+#                        headline size on 2 and 8 GPUs (see the module docstring).
 # memory="gather"      : one forward launch per rank; its fetcher warps pull all W-1 peer slots into a W-slot gather
-#                        buffer (transient, shared by all layers); workspace O(n) per rank.  The head-dim-64 / two-kernel
-#                        backward always gathers.
-CONFIG = {"backward": "fused", "memory": "ring"}
+#                        buffer (transient, shared by all layers); workspace O(n) per rank.  Fewer launches: better for
+#                        short shards, where the one-kernel backward's per-launch ramp shows (8 hops x 8192 keys, h=16:
+#                        726 vs 826 TFLOP/s).  The head-dim-64 / two-kernel backward always gathers.
+# memory="auto"        : "ring" when one rank's K/V slot is at least AUTO_RING_SLOT_BYTES (the gather would then cost
+#                        W x 2 slots of HBM), else "gather".
+AUTO_RING_SLOT_BYTES = 128 << 20
+CONFIG = {"backward": "fused", "memory": "auto"}
+
+
+def _use_hop_window(slot_bytes: int) -> bool:
+    mode = CONFIG["memory"]
+    assert mode in ("auto", "ring", "gather"), mode
+    return mode == "ring" or (mode == "auto" and slot_bytes >= AUTO_RING_SLOT_BYTES)
+
 
 
 def _count(n: int = 1) -> None:
@@ -241,7 +252,7 @@ class RingFlashAttentionCUDAFunction(Function):
         ready = torch.zeros(ring_size, dtype=torch.int32, device=dev)
         peers = [0] * ring_size
         kbits = None
-        hop_mode = use_ring and CONFIG["memory"] == "ring"
+        hop_mode = use_ring and _use_hop_window(2 * b * hk * n_k * d_pad * 2)
         with nvtx_range("rab.fwd.pack+barrier"):
             if hop_mode:
                 ws = get_workspace(ring_size, dev)
@@ -316,7 +327,8 @@ class RingFlashAttentionCUDAFunction(Function):
 
         ws = None
         kv_own_ptrs, kv_bytes = None, 0
-        hop_mode = use_ring and CONFIG["memory"] == "ring" and d_pad == 128 and CONFIG["backward"] == "fused"
+        hop_mode = (use_ring and d_pad == 128 and CONFIG["backward"] == "fused"
+                    and _use_hop_window(2 * b * hk * n_k * d_pad * 2))
         if hop_mode:
             ws = get_workspace(ring_size, dev)
             own, kv_own_ptrs, kv_bytes = _own_slot_workspace(ws, b, hk, n_k, d_pad, dt)
