@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--fwd-only", action="store_true", help="diagnostic only (not a valid headline number)")
     ap.add_argument("--memory", default="auto", choices=["auto", "gather", "ring"],
                     help="ring_cuda.CONFIG['memory']: 'ring' = per-hop launches against a 2-slot K/V window (O(n/W) "
-                         "workspace); 'auto' picks it for K/V slots >= 128 MiB per rank (the headline config at any N)")
+                         "workspace); 'auto' picks it for K/V slots >= 256 MiB per rank (the headline config at any N)")
     return ap.parse_args()
 
 
@@ -317,8 +317,7 @@ def main():
             steps = max(2, min(steps, int(args.ref_budget_s / max(per, 1e-6))))
 
         fetch_times = None
-        hop_window = args.impl == "ours" and world > 1 and (
-            args.memory == "ring" or (args.memory == "auto" and 2 * B * n_ * HK * D * 2 >= (128 << 20)))
+        hop_window = args.impl == "ours" and world > 1 and ring_cuda._use_hop_window(2 * B * n_ * HK * D * 2)
         if args.impl == "ours" and world > 1 and not hop_window:
             fetch_times = torch.zeros(256, 2, dtype=torch.int64, device=dev)
             torch.ops.rab.set_fetch_timing(fetch_times)

@@ -5,7 +5,7 @@ Public surface mirrors reference ring_flash_attention_cuda.py:353-371 (``ring_fl
 
 Forward, per rank (no host synchronisation, no NCCL on the hot path), ``CONFIG["memory"]``:
 
-``"ring"`` (what the default ``"auto"`` picks for K/V slots >= 128 MiB per rank) — O(n / W) workspace, like the reference's send/recv ring (ring_flash_attention_cuda.py:128-178):
+``"ring"`` (what the default ``"auto"`` picks for K/V slots >= 256 MiB per rank) — O(n / W) workspace, like the reference's send/recv ring (ring_flash_attention_cuda.py:128-178):
 
     pack_kv (K,V -> head-major) into this rank's own SYMMETRIC slot -> device barrier -> one tcgen05 flash-attention
     launch per ring hop; hop 0 reads the own slot in place, hop s reads a 2-slot window that the COPY ENGINES fill up
@@ -78,9 +78,10 @@ LAUNCHES = {"count": 0}
 #                        buffer (transient, shared by all layers); workspace O(n) per rank.  Fewer launches: better for
 #                        short shards, where the one-kernel backward's per-launch ramp shows (8 hops x 8192 keys, h=16:
 #                        726 vs 826 TFLOP/s).  The head-dim-64 / two-kernel backward always gathers.
-# memory="auto"        : "ring" when one rank's K/V slot is at least AUTO_RING_SLOT_BYTES (the gather would then cost
-#                        W x 2 slots of HBM), else "gather".
-AUTO_RING_SLOT_BYTES = 128 << 20
+# memory="auto"        : "ring" when one rank's K/V slot is at least AUTO_RING_SLOT_BYTES, else "gather".  Measured on 2
+#                        GPUs: 128 MiB slots (S=16384, h=32) ring 1441 vs gather 1546 TFLOP/s — ~90 us of ramp per extra
+#                        launch against 5 ms steps; 2 GiB slots (S=262144) 1656 vs 1646; 8 GPUs, 512 MiB slots 6369 vs 6174.
+AUTO_RING_SLOT_BYTES = 256 << 20
 CONFIG = {"backward": "fused", "memory": "auto"}
 
 
