@@ -248,3 +248,26 @@ def test_argument_validation_names_the_offending_argument():
     with pytest.raises(ValueError, match="mask must be bool"):
         check_attention_inputs(q, k, k, torch.ones(2, 7, dtype=torch.bool))
     check_attention_inputs(q, k, k, torch.ones(2, 8, dtype=torch.bool))
+
+
+def test_memory_mode_selection():
+    """CONFIG["memory"]: "auto" switches to the hop window at AUTO_RING_SLOT_BYTES; forward and backward decide from
+    the same slot size, so they always agree."""
+    from ring_attention_pytorch_b200.ops import ring_cuda
+
+    old = ring_cuda.CONFIG["memory"]
+    try:
+        ring_cuda.CONFIG["memory"] = "auto"
+        assert not ring_cuda._use_hop_window(ring_cuda.AUTO_RING_SLOT_BYTES - 1)
+        assert ring_cuda._use_hop_window(ring_cuda.AUTO_RING_SLOT_BYTES)
+        # headline config: S=262144, h=32, d=128 on 8 GPUs -> 512 MiB slots -> hop window
+        assert ring_cuda._use_hop_window(2 * (262144 // 8) * 32 * 128 * 2)
+        ring_cuda.CONFIG["memory"] = "ring"
+        assert ring_cuda._use_hop_window(1)
+        ring_cuda.CONFIG["memory"] = "gather"
+        assert not ring_cuda._use_hop_window(1 << 40)
+        ring_cuda.CONFIG["memory"] = "bogus"
+        with pytest.raises(AssertionError):
+            ring_cuda._use_hop_window(1)
+    finally:
+        ring_cuda.CONFIG["memory"] = old
