@@ -28,7 +28,6 @@ import statistics
 import subprocess
 import sys
 import threading
-import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

@@ -14,7 +14,6 @@ maps instead of bucket bookkeeping:
 """
 from __future__ import annotations
 
-import math
 from typing import Optional
 
 import torch
