@@ -526,10 +526,20 @@ void tree_decode(const Tensor& q, const c10::optional<Tensor>& k, const c10::opt
   p.q_kind = q.scalar_type() == at::kBFloat16 ? 0 : (q.scalar_type() == at::kHalf ? 1 : 2);
   TORCH_CHECK(p.q_kind != 2 || q.scalar_type() == at::kFloat, "q must be bf16, fp16 or fp32");
   int n = 0;
+  int64_t kv_plane_stride = 0;  // elements between consecutive (batch, kv head) planes
   if (k.has_value()) {
-    TORCH_CHECK(v.has_value() && k->is_contiguous() && v->is_contiguous() && k->dim() == 4 && k->sizes() == v->sizes());
+    TORCH_CHECK(v.has_value() && k->dim() == 4 && k->sizes() == v->sizes() && k->strides() == v->strides());
     TORCH_CHECK(k->size(0) == b && k->size(1) == kv_heads && k->size(3) == d);
     n = k->size(2);
+    // a growing cache passes the filled prefix [b, hk, :n, d] of a [b, hk, capacity, d] buffer: rows stay dense, the
+    // (batch, head) planes keep the buffer's stride.  Only the tensor-core kernel takes that (it sees K / V through
+    // tensor maps); the CUDA-core kernel needs dense planes.
+    const bool rows_dense = k->stride(3) == 1 && k->stride(2) == d && k->stride(0) == kv_heads * k->stride(1) &&
+                            k->stride(1) >= (int64_t)n * d;
+    TORCH_CHECK(k->is_contiguous() || (tensor_core && rows_dense),
+                "k / v must be contiguous [b, hk, n, d] (or, for the tensor-core kernel, a prefix view of a [b, hk, "
+                "capacity, d] buffer)");
+    kv_plane_stride = k->is_contiguous() ? (int64_t)n * d : k->stride(1);  // strides of size-1 dims are arbitrary
     if (k->scalar_type() == at::kBFloat16) p.kv_kind = 0;
     else if (k->scalar_type() == at::kHalf) p.kv_kind = 1;
     else if (k->scalar_type() == at::kFloat8_e4m3fn) p.kv_kind = 2;
@@ -586,7 +596,8 @@ void tree_decode(const Tensor& q, const c10::optional<Tensor>& k, const c10::opt
     // K, V [b*hk, n, d] -> dims (d, n, b*hk); box = one 128-byte wide, 128-key sub-tile
     const uint64_t eb = p.kv_kind == 2 ? 1 : 2;
     uint64_t dims[3] = {(uint64_t)d, (uint64_t)n, (uint64_t)b * kv_heads};
-    uint64_t strides[2] = {(uint64_t)d * eb, (uint64_t)n * d * eb};
+    uint64_t strides[2] = {(uint64_t)d * eb, (uint64_t)kv_plane_stride * eb};
+    TORCH_CHECK(strides[1] % 16 == 0, "k / v plane stride must be a multiple of 16 bytes");
     uint32_t box[3] = {(uint32_t)(128 / eb), 128, 1};
     auto mk = [&](const void* base) {
       if (p.kv_kind == 2) return rab::make_tmap_u8(base, 3, dims, strides, box, rab::TmapSwizzle::B128);

@@ -124,6 +124,17 @@ def uses_nvls(q: Tensor) -> bool:
 
 
 @torch.no_grad()
+def _is_cache_prefix(t: Tensor) -> bool:
+    """[b, hk, n, d] with dense rows and uniformly strided (batch, head) planes: the filled prefix of a growing
+    [b, hk, capacity, d] cache.  The tensor-core kernel reads it in place (tensor-map plane stride), no copy."""
+    b, hk, n, d = t.shape
+    sb, sh, sn, sd = t.stride()
+    if t.is_contiguous():
+        return True
+    return (b > 1 and hk > 1 and sd == 1 and sn == d and sb == hk * sh and sh >= n * d
+            and (sh * t.element_size()) % 16 == 0)
+
+
 def tree_decode_cuda(
     q: Tensor,
     k: Optional[Tensor],
@@ -137,6 +148,8 @@ def tree_decode_cuda(
     out: Optional[Tensor] = None,
 ) -> Tensor:
     """q [b, h, 1, d] (bf16 / fp16 / fp32); k, v [b, hk, n, d] this rank's shard (bf16 / fp16 / float8_e4m3fn) or None.
+    k / v may be the filled prefix ``cache[:, :, :n]`` of a larger ``[b, hk, capacity, d]`` buffer: the tensor-core kernel
+    (head dim 128, n >= 128) reads it in place; other cases are made contiguous first.
 
     ``k_scale`` / ``v_scale``: optional fp32 dequantisation scales for the fp8 path, either per (batch, kv head)
     (``numel == b*hk``) or block-scaled ``[b*hk, n_blocks]`` with one scale per ``scale_block_keys`` keys
@@ -156,7 +169,6 @@ def tree_decode_cuda(
     if k is not None and k.shape[-2] > 0:
         if k.dtype == torch.float32:
             k, v = k.to(torch.bfloat16), v.to(torch.bfloat16)
-        k, v = k.contiguous(), v.contiguous()
         hk, n = k.shape[1], k.shape[2]
     else:
         k = v = None
@@ -165,6 +177,8 @@ def tree_decode_cuda(
     tc = CONFIG["tensor_core"]
     # a 128-key tile of the tensor-core kernel must lie inside one scale block
     use_tc = tc in ("auto", True, "on") and d == 128 and n >= 128 and scale_block_keys % 128 == 0
+    if k is not None and not (use_tc and _is_cache_prefix(k) and v.stride() == k.stride()):
+        k, v = k.contiguous(), v.contiguous()  # no-op for dense inputs
     gm = (4 if g <= 4 else 16) if use_tc else 4  # query heads per work unit (tensor-core kernel: template bound GM)
     groups = b * hk * ((g + gm - 1) // gm)
     resident = int(ops.tree_decode_max_ctas(d, kv_kind, use_tc))

@@ -693,3 +693,26 @@ def test_tree_decode_is_cuda_graph_capturable(fp8):
         torch.cuda.synchronize()
         ref = _dense_decode(q, kk.float(), vv.float())
         assert (out.float() - ref).abs().max() < (6e-2 if fp8 else 2e-2), it
+
+
+@pytest.mark.parametrize("fp8", [False, True])
+def test_tree_decode_reads_a_growing_cache_in_place(fp8):
+    """k / v = filled prefix of a [b, hk, capacity, d] buffer: the tensor-core kernel reads it through the tensor map's
+    plane stride (no copy) and matches the dense copy of the same prefix, step after step."""
+    from ring_attention_pytorch_b200.ops import tree_decode_cuda as tdc
+
+    torch.manual_seed(0)
+    b, h, hk, d, cap = 3, 8, 2, 128, 1000
+    dt = torch.float8_e4m3fn if fp8 else torch.bfloat16
+    kc = (torch.randn(b, hk, cap, d, device="cuda") * (0.5 if fp8 else 1.0)).to(dt)
+    vc = (torch.randn(b, hk, cap, d, device="cuda") * (0.5 if fp8 else 1.0)).to(dt)
+    q = torch.randn(b, h, 1, d, device="cuda", dtype=torch.bfloat16)
+    sc = torch.ones(b * hk, device="cuda") if fp8 else None
+    for n in (128, 300, 777, cap):
+        kp, vp = kc[:, :, :n], vc[:, :, :n]
+        assert tdc._is_cache_prefix(kp) and (n == cap or not kp.is_contiguous())
+        got = tdc.tree_decode_cuda(q, kp, vp, dim_v=d, k_scale=sc, v_scale=sc)
+        want = tdc.tree_decode_cuda(q, kp.contiguous(), vp.contiguous(), dim_v=d, k_scale=sc, v_scale=sc)
+        assert (got.float() - want.float()).abs().max() < 2e-3, n  # same kernel, same tiles: only the source stride differs
+        ref = _dense_decode(q.float(), kp.float(), vp.float())
+        assert (got.float() - ref).abs().max() < (6e-2 if fp8 else 2e-2)
