@@ -528,7 +528,8 @@ void tree_decode(const Tensor& q, const c10::optional<Tensor>& k, const c10::opt
   int n = 0;
   int64_t kv_plane_stride = 0;  // elements between consecutive (batch, kv head) planes
   if (k.has_value()) {
-    TORCH_CHECK(v.has_value() && k->dim() == 4 && k->sizes() == v->sizes() && k->strides() == v->strides());
+    TORCH_CHECK(v.has_value() && k->dim() == 4 && k->sizes() == v->sizes());
+    TORCH_CHECK(k->is_contiguous() ? v->is_contiguous() : k->strides() == v->strides(), "k and v must share a layout");
     TORCH_CHECK(k->size(0) == b && k->size(1) == kv_heads && k->size(3) == d);
     n = k->size(2);
     // a growing cache passes the filled prefix [b, hk, :n, d] of a [b, hk, capacity, d] buffer: rows stay dense, the
