@@ -701,6 +701,7 @@ def test_tree_decode_reads_a_growing_cache_in_place(fp8):
     plane stride (no copy) and matches the dense copy of the same prefix, step after step."""
     from ring_attention_pytorch_b200.ops import tree_decode_cuda as tdc
 
+    tdc.CONFIG["tensor_core"] = "auto"  # earlier tests may have left the CUDA-core kernel selected
     torch.manual_seed(0)
     b, h, hk, d, cap = 3, 8, 2, 128, 1000
     dt = torch.float8_e4m3fn if fp8 else torch.bfloat16
