@@ -378,7 +378,7 @@ class RingTransformer(Module):
         striped_ring_attn: bool = False,
         ring_seq_size: int = 512,
         auto_shard_seq: Optional[bool] = None,
-        max_lookback_seq_len: Union[Tuple[Optional[int], ...], int, None] = None,
+        max_lookback_seq_len: Union[tuple[Optional[int], ...], int, None] = None,
         rotary_embed_theta: int = 10000,
         ignore_index: int = -1,
         force_regular_attn: bool = False,
