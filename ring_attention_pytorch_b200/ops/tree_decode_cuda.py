@@ -123,7 +123,6 @@ def uses_nvls(q: Tensor) -> bool:
     return key in _cache and _cache[key].mc_partial_ptr != 0
 
 
-@torch.no_grad()
 def _is_cache_prefix(t: Tensor) -> bool:
     """[b, hk, n, d] with dense rows and uniformly strided (batch, head) planes: the filled prefix of a growing
     [b, hk, capacity, d] cache.  The tensor-core kernel reads it in place (tensor-map plane stride), no copy."""
@@ -135,6 +134,7 @@ def _is_cache_prefix(t: Tensor) -> bool:
             and (sh * t.element_size()) % 16 == 0)
 
 
+@torch.no_grad()
 def tree_decode_cuda(
     q: Tensor,
     k: Optional[Tensor],
