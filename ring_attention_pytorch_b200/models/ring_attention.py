@@ -17,7 +17,7 @@ Differences, all of them fixes of behaviour the reference gets wrong (SURVEY.md 
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple, Union
+from typing import Optional, Union
 
 import torch
 import torch.nn.functional as F
@@ -89,47 +89,38 @@ class RingRotaryEmbedding(Module):
         return torch.cat((freqs, freqs), dim=-1)
 
 
-def rotate_half(x: Tensor) -> Tensor:
-    x1, x2 = x.chunk(2, dim=-1)
-    return torch.cat((-x2, x1), dim=-1)
-
-
 @torch.autocast("cuda", enabled=False)
 def apply_rotary_pos_emb(pos: Tensor, t: Tensor, head_dim_first: bool = False) -> Tensor:
-    """reference ring_attention.py:167-172; ``pos`` is [n, d], ``t`` is [b, n, h, d] (or [b, h, n, d])."""
-    if not head_dim_first:
-        pos = pos[:, None, :]
-    out = t.float() * pos.cos() + rotate_half(t.float()) * pos.sin()
+    """Rotate feature pairs ``(i, i + d/2)`` of ``t`` ([b, n, h, d], or [b, h, n, d] with ``head_dim_first``) by the
+    angles ``pos`` [n, d] (both halves of ``pos`` carry the same d/2 angles).  Same convention as the reference
+    (ring_attention.py:160-172) and as ``csrc/elementwise_sm100.cu::rotary_kernel``; computed in fp32."""
+    ang = pos if head_dim_first else pos.unsqueeze(1)
+    half = t.shape[-1] // 2
+    cos, sin = ang.cos(), ang.sin()
+    lo, hi = t[..., :half].float(), t[..., half:].float()
+    out = torch.cat((lo * cos[..., :half] - hi * sin[..., :half], hi * cos[..., half:] + lo * sin[..., half:]), dim=-1)
     return out.to(t.dtype)
 
 
 # ------------------------------------------------------------------------------------------------
 # padding and batch <-> sequence resharding (reference ring_attention.py:176-279)
 # ------------------------------------------------------------------------------------------------
-def pad_at_dim(t: Tensor, pad: Tuple[int, int], *, dim: int = -1, value=0.0) -> Tensor:
-    dims_from_right = (-dim - 1) if dim < 0 else (t.ndim - dim - 1)
-    zeros = (0, 0) * dims_from_right
-    return F.pad(t, (*zeros, *pad), value=value)
-
-
-def pad_to_multiple(x: Tensor, length: int, pad_value=0):
-    seq_len = x.shape[1]
-    remainder = seq_len % length
-    if remainder == 0:
-        return x, 0
-    pad_length = length - remainder
-    return pad_at_dim(x, (0, pad_length), value=pad_value, dim=1), pad_length
+def _pad_tokens(t: Tensor, multiple: int, value) -> Tensor:
+    """Right-pad axis 1 (tokens) of ``t`` to the next multiple of ``multiple``."""
+    missing = -t.shape[1] % multiple
+    if missing == 0:
+        return t
+    filler = t.new_full((t.shape[0], missing, *t.shape[2:]), value)
+    return torch.cat((t, filler), dim=1)
 
 
 def maybe_pad_seq_and_mask(x: Tensor, mask: Optional[Tensor], seq_size: int):
-    shape = x.shape[:2]
-    x, pad_length = pad_to_multiple(x, seq_size)
-    if pad_length == 0:
+    """Pad tokens (and the key mask, created on demand so that the padding is masked out) to a multiple of ``seq_size``."""
+    if x.shape[1] % seq_size == 0:
         return x, mask
-    if not exists(mask):
-        mask = torch.ones(shape, device=x.device, dtype=torch.bool)
-    mask, _ = pad_to_multiple(mask, seq_size, pad_value=False)
-    return x, mask
+    if mask is None:
+        mask = torch.ones(x.shape[:2], device=x.device, dtype=torch.bool)
+    return _pad_tokens(x, seq_size, 0), _pad_tokens(mask, seq_size, False)
 
 
 def stripe(t: Tensor, ring_seq_size: int) -> Tensor:
@@ -188,15 +179,17 @@ def sharded_seq_to_sharded_batch(logits: Tensor, sizes: Tensor, num_sharded_batc
 # layers
 # ------------------------------------------------------------------------------------------------
 class RMSNorm(Module):
-    """reference ring_attention.py:470-477"""
+    """x / rms(x) * gamma, written as unit-normalise times sqrt(dim) (parameter name ``gamma`` as in the reference,
+    ring_attention.py:470-477, so that its checkpoints load)."""
 
     def __init__(self, dim: int):
         super().__init__()
-        self.scale = dim ** 0.5
         self.gamma = nn.Parameter(torch.ones(dim))
+        self.sqrt_dim = float(dim) ** 0.5
 
     def forward(self, x: Tensor) -> Tensor:
-        return F.normalize(x, dim=-1) * self.scale * self.gamma
+        unit = x / x.norm(dim=-1, keepdim=True).clamp_min(1e-12)  # what F.normalize computes
+        return unit * (self.sqrt_dim * self.gamma)
 
 
 class BlockwiseSequential(nn.Sequential):
