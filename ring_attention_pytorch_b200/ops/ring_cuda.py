@@ -91,7 +91,6 @@ def _use_hop_window(slot_bytes: int) -> bool:
     return mode == "ring" or (mode == "auto" and slot_bytes >= AUTO_RING_SLOT_BYTES)
 
 
-
 def _count(n: int = 1) -> None:
     LAUNCHES["count"] += n
 

@@ -271,3 +271,19 @@ def test_memory_mode_selection():
             ring_cuda._use_hop_window(1)
     finally:
         ring_cuda.CONFIG["memory"] = old
+
+
+def test_decode_cache_prefix_detection():
+    """Which K/V layouts the tensor-core decode kernel may read in place (tensor-map plane stride) instead of copying."""
+    from ring_attention_pytorch_b200.ops.tree_decode_cuda import _is_cache_prefix
+
+    cache = torch.zeros(3, 2, 1000, 128, dtype=torch.bfloat16)
+    assert _is_cache_prefix(cache)                       # dense
+    assert _is_cache_prefix(cache[:, :, :300])           # filled prefix of a growing cache
+    assert _is_cache_prefix(cache[:, :, 200:500])        # a sequence chunk (tree_attn_decode(shard_kv_seq=True))
+    assert not _is_cache_prefix(cache[:, :, ::2])        # rows not dense
+    assert not _is_cache_prefix(cache[..., :64])         # head dim sliced
+    assert not _is_cache_prefix(cache.transpose(0, 1)[:, :, :300])  # planes not uniformly strided
+    assert not _is_cache_prefix(torch.zeros(3, 1000, 2, 128).transpose(1, 2))  # [b, n, h, d] storage
+    odd = torch.zeros(3, 2, 1001, 4, dtype=torch.float8_e4m3fn)  # plane stride 4004 B: not 16-byte aligned
+    assert not _is_cache_prefix(odd[:, :, :300])
