@@ -18,9 +18,10 @@ Forward, per rank (no host synchronisation, no NCCL on the hot path), ``CONFIG["
     kernel: flash attention over every hop while its fetcher warps pull the other ranks' K/V slots over NVLink
     (bulk TMA) into the local gather buffer; O / max / sum never leave TMEM and registers
 
-Measured at the headline config (S=262144, h=32, fwd+bwd): 2 GPUs 1656 vs 1646 TFLOP/s, 8 GPUs 6369 vs 6174 TFLOP/s
-("ring" vs "gather"; the copy engines move the bytes without taking shared-memory bandwidth from the MMA pipeline),
-and S = 4 194 304 on 8 GPUs runs in "ring" (96 GB per GPU) where the W-slot gather alone would need 137 GB.
+Measured at the headline config (S=262144, h=32, fwd+bwd): same box, back to back, 2 GPUs: 1656 ("ring") vs 1646
+("gather") TFLOP/s, i.e. on par; 8 GPUs: 6369 ("ring") against 6174 ("gather", measured earlier in the round on another
+box, so inside box-to-box variation).  What "ring" buys is memory: S = 4 194 304 on 8 GPUs runs (96 GB per GPU) where the
+W-slot gather alone would need 137 GB.  At short shards the extra launches cost (see ``CONFIG`` below).
 
 Only q, k, v, o and the log-sum-exp are saved for the backward (O(n / W) activation memory per layer; the reference
 saves the same, ring_flash_attention_cuda.py:188-198).  The workspaces are transient and shared by all layers.
@@ -72,15 +73,15 @@ LAUNCHES = {"count": 0}
 # backward="two_kernel": the dQ + dK/dV kernel pair (7 GEMMs, no atomics, deterministic); head dim 64 always uses it.
 # memory="ring"        : one launch per ring hop against a 2-slot window that the copy engines fill ahead of the
 #                        kernels; the online-softmax state (forward) and the fp32 accumulators (backward, head dim 128)
-#                        carry over between the launches.  Workspace O(n / W) per rank; faster than "gather" at the
-#                        headline size on 2 and 8 GPUs (see the module docstring).
+#                        carry over between the launches.  Workspace O(n / W) per rank; on par with "gather" at the
+#                        headline size (see the module docstring).
 # memory="gather"      : one forward launch per rank; its fetcher warps pull all W-1 peer slots into a W-slot gather
 #                        buffer (transient, shared by all layers); workspace O(n) per rank.  Fewer launches: better for
 #                        short shards, where the one-kernel backward's per-launch ramp shows (8 hops x 8192 keys, h=16:
 #                        726 vs 826 TFLOP/s).  The head-dim-64 / two-kernel backward always gathers.
 # memory="auto"        : "ring" when one rank's K/V slot is at least AUTO_RING_SLOT_BYTES, else "gather".  Measured on 2
 #                        GPUs: 128 MiB slots (S=16384, h=32) ring 1441 vs gather 1546 TFLOP/s — ~90 us of ramp per extra
-#                        launch against 5 ms steps; 2 GiB slots (S=262144) 1656 vs 1646; 8 GPUs, 512 MiB slots 6369 vs 6174.
+#                        launch against 5 ms steps; 2 GiB slots (S=262144) 1656 vs 1646 (same box, back to back).
 AUTO_RING_SLOT_BYTES = 256 << 20
 CONFIG = {"backward": "fused", "memory": "auto"}
 
