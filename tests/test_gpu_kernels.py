@@ -36,6 +36,13 @@ def test_umma_descriptors(mode, variant):
     assert res["ok"], res
 
 
+def test_umma_descriptor_mn_major_a_operand():
+    """A operand read MN-major from shared memory with B written by the kernel's own threads: the operand forms of the
+    one-kernel backward's dQ^T = K^T dS^T (validated on B200 in round 2: profiles/dev_check_r2_fused_bwd_v2.log)."""
+    res = _cases().case_probe_mn_a()
+    assert res["ok"], res
+
+
 FWD_CASES = {
     "d128": dict(),
     "d128_n128_h1": dict(n=128, h=1),
