@@ -38,7 +38,7 @@ def test_umma_descriptors(mode, variant):
 
 def test_umma_descriptor_mn_major_a_operand():
     """A operand read MN-major from shared memory with B written by the kernel's own threads: the operand forms of the
-    one-kernel backward's dQ^T = K^T dS^T (validated on B200 in round 2: profiles/dev_check_r2_fused_bwd_v2.log)."""
+    one-kernel backward's dQ^T = K^T dS^T (validated on B200 in round 2: profiles/dev_check_r2_fused_bwd_v1.log)."""
     res = _cases().case_probe_mn_a()
     assert res["ok"], res
 
