@@ -55,8 +55,8 @@ setup(
     packages=find_packages(include=["ring_attention_pytorch_b200", "ring_attention_pytorch_b200.*"]),
     package_data={"ring_attention_pytorch_b200": ["_C.so", "csrc/*"]},
     python_requires=">=3.10",
-    install_requires=["torch>=2.6", "einops>=0.8.0"],
-    extras_require={"test": ["pytest", "click"]},
+    install_requires=["torch>=2.6", "beartype"],  # beartype is optional at run time (utils/validate.py)
+    extras_require={"test": ["pytest", "hypothesis", "click"]},
     cmdclass={"build_ext": build_ext, "build_py": build_py, "build_native": build_native},
     zip_safe=False,
 )
